@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- Heston FFT slices/sec (param x maturity, N=4096) on 1..8 B200, CPU beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sets P]
+
+A "step" is one pass of the hot path over one batch of synthetic input: BASELINE.json
+config 3, the batched calibration objective + finite-difference Jacobian (as J^T J / J^T r
+normal-equation blocks) over P = 65,536 parameter sets x 32 maturities x 50 strikes,
+N = 4096, eta = 0.25, alpha = 0.75, per GPU (weak scaling: every rank prices its own P sets;
+the only collective is the NCCL all-gather of the 22-double result rows).  One step = one
+launch of the fused kernel = P x 32 x (1 + 5) slice evaluations; `value` counts all six.
+
+Prints ONE JSON line (rank 0).  `--impl reference` instead times the reference's own CPU
+implementation (oracle/_ref = its heston.cpp compiled unmodified, OpenMP over options) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+S0, R, Q = 100.0, 0.05, 0.02
+TRUTH = np.array([2.0, 0.04, 0.3, -0.7, 0.04])
+LB = np.array([0.1, 0.01, 0.01, -0.99, 0.01])  # HestonCalibrator.DEFAULT_BOUNDS
+UB = np.array([10.0, 1.0, 2.0, 0.99, 1.0])
+N_GRID, ETA, ALPHA = 4096, 0.25, 0.75
+N_MAT, N_STRIKE = 32, 50
+METRIC = "Heston FFT slices/sec (param x maturity, N=4096)"
+# SURVEY.md 8(d), frozen convention W1: algorithmic FLOPs of one slice (N=4096, S=50)
+FLOPS_PER_SLICE = 4096 * 700 + 5 * 4096 * 12 + 12 * 50  # = 3,113,560
+# algorithmic HBM bytes per slice evaluation: 40 B of parameters per set and 22 doubles out per set,
+# spread over the 6 x 32 slice evaluations of that set
+BYTES_PER_SLICE = (40.0 + 22 * 8.0) / (6 * N_MAT)
+
+
+def surface():
+    K = np.tile(np.linspace(80.0, 120.0, N_STRIKE), N_MAT)
+    T = np.repeat(np.linspace(0.1, 1.0, N_MAT), N_STRIKE)
+    return K, T
+
+
+def sobol_sets(P, skip=0):
+    from scipy.stats import qmc
+
+    s = qmc.Sobol(d=5, seed=42)
+    if skip:
+        s.fast_forward(skip)
+    return LB + (UB - LB) * s.random(P)
+
+
+def fd_variants(X):
+    """Base + 5 forward-difference perturbed sets per row (SciPy 2-point rule with bounds)."""
+    rstep = 1.4901161193847656e-08
+    out = np.repeat(X[:, None, :], 6, axis=1)
+    for c in range(5):
+        x = X[:, c]
+        h = rstep * np.where(x >= 0, 1.0, -1.0) * np.maximum(1.0, np.abs(x))
+        lower, upper = x - LB[c], UB[c] - x
+        xn = x + h
+        violated = (xn < LB[c]) | (xn > UB[c])
+        fitting = np.abs(h) <= np.maximum(lower, upper)
+        h = np.where(violated & fitting, -h, h)
+        h = np.where(~fitting, np.where(upper >= lower, upper, -lower), h)
+        out[:, c + 1, c] = x + h
+    return out.reshape(-1, 5)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_rate(seconds_budget, n_sets_hint=None):
+    """Reference CPU path (oracle/_ref: heston.cpp unmodified, price_options with OpenMP over options)
+    on whole (set x 32-maturity) surfaces until `seconds_budget` is spent.  -> (slices/s, info)."""
+    from oracle.oracle import Reference
+
+    ref = Reference()
+    K, T = surface()
+    cores = ref.num_threads()
+    rows = fd_variants(sobol_sets(4096)[:512])
+    ref.price_surface_batch(rows[:1], K, T, S0, R, Q)  # warm
+    done, t0 = 0, time.perf_counter()
+    chunk = n_sets_hint or max(1, cores // 8)
+    while True:
+        ref.price_surface_batch(rows[done:done + chunk], K, T, S0, R, Q)
+        done += chunk
+        el = time.perf_counter() - t0
+        if el >= seconds_budget or done + chunk > len(rows):
+            break
+    return done * N_MAT / el, {"cores": cores, "kind": "reference", "seconds": round(el, 3),
+                               "sample": f"{done} parameter-set evaluations x {N_MAT} maturities x {N_STRIKE} strikes "
+                                         f"through the reference's HestonModel::price_options (1023-point quadrature "
+                                         f"per option, OpenMP over options)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2.0, min(8.0, 120.0 / max(1, args.steps + args.warmup)))
+    rates = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        rate, info = cpu_reference_rate(per_step)
+        if i >= args.warmup:
+            rates.append(rate)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.sets),
+        "cpu_baseline": {"value": value, "unit": "slices/s", "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(P):
+    return {"workload": f"C3: batched calibration objective + finite-difference Jacobian (J^T J, J^T r blocks), "
+                        f"{P} parameter sets x {N_MAT} maturities x {N_STRIKE} strikes per GPU, N={N_GRID}, "
+                        f"eta={ETA}, alpha={ALPHA}; 6 slice evaluations per (set, maturity)",
+            "sets_per_gpu": P, "maturities": N_MAT, "strikes": N_STRIKE, "n_grid": N_GRID,
+            "slice_evals_per_step_per_gpu": P * N_MAT * 6, "mode": "fft",
+            "l2": "L2 flushed (256 MiB write) between timed steps; per-step CUDA events on the launch stream"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from pde_b200 import BatchPricer, launch_count, measure_fp64_peak
+    from pde_b200.sharding import init_from_env
+
+    rank, world, local = init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    dev = torch.device("cuda", local)
+    P = args.sets
+    K, T = surface()
+    pricer = BatchPricer("fft", N_GRID, ETA, ALPHA, device=local)
+    # synthetic market: model prices at the truth, 0.1% relative noise, 0.01 floor (generator's convention)
+    pricer.set_surface(K, T, True, None, S0=S0, r=R, q=Q)
+    mk = pricer.price_host(TRUTH[None, :])[0]
+    mk = np.maximum(mk * (1 + 0.001 * np.random.default_rng(42).normal(size=mk.size)), 0.01)
+    pricer.set_surface(K, T, True, mk, S0=S0, r=R, q=Q).set_bounds(LB, UB)
+
+    X_host = torch.from_numpy(sobol_sets(P, skip=rank * P)).pin_memory()
+    X = X_host.to(dev)
+    gathered = torch.empty((world * P, 22), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        out = pricer.normal_equations(X)
+        if world > 1:  # loss + Jacobian-block all-gather over NVLink (multi-start / population drivers)
+            dist.all_gather_into_tensor(gathered, out)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    peak = measure_fp64_peak(local, 0.5)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = launch_count()
+    t_wall = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        out = step()
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    slices_step = world * P * N_MAT * 6
+    value = slices_step * args.steps / (ms * 1e-3)
+
+    # e2e: the public host-buffer call (pinned in/out, H2D + D2H inside the timed region)
+    Xh = X_host.numpy()
+    pricer.normal_equations_host(Xh[: min(P, 1024)])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = pricer.normal_equations_host(Xh)
+    torch.cuda.synchronize(dev)
+    te = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([te], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e = slices_step * args.steps / te
+    assert np.isfinite(res[:, 0]).all()
+
+    if rank == 0:
+        achieved = (P * N_MAT * 6 * FLOPS_PER_SLICE) / (ms / args.steps * 1e-3) / 1e12  # per GPU, TFLOP/s
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
+        hbm_achieved = (P * N_MAT * 6 * BYTES_PER_SLICE) / (ms / args.steps * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(P),
+            "base_slices_per_s": value / 6.0,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "slices/s", "h2d_bytes_per_step": int(world * P * 5 * 8),
+                    "d2h_bytes_per_step": int(world * P * 22 * 8)},
+            "gpu_launches": int(launches),
+            "wall_s_timed_region": t_wall,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "peak_source": "DFMA probe (hb_measure_fp64_peak) run in this process; "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "flops_per_slice_W1": FLOPS_PER_SLICE,
+                         "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak,
+                                 "frac": hbm_achieved / hbm_peak, "bytes_per_slice": BYTES_PER_SLICE}},
+        }
+        if world == 1 and not args.no_cpu:
+            rate, info = cpu_reference_rate(12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "slices/s", "cores": info["cores"], "kind": info["kind"],
+                                    "sample": info["sample"]}
+            try:
+                from oracle.oracle import MODE_FFT, Oracle
+
+                orc = Oracle()
+                rows = fd_variants(sobol_sets(64))
+                t0 = time.perf_counter()
+                n_done = 0
+                while time.perf_counter() - t0 < 6.0 and n_done < len(rows):
+                    orc.objective_batch(MODE_FFT, rows[n_done:n_done + 32], K, T, True, mk, S0, R, Q)
+                    n_done += 32
+                el = time.perf_counter() - t0
+                line["cpu_baseline"]["port_fft"] = {"value": n_done * N_MAT / el, "unit": "slices/s",
+                                                    "cores": orc.num_threads(), "kind": "port",
+                                                    "sample": f"{n_done} parameter-set evaluations x {N_MAT} maturities, "
+                                                              f"C restatement of the N=4096 Carr-Madan FFT path, OpenMP over sets"}
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"]["port_fft"] = {"error": str(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sets", type=int, default=65536, help="parameter sets per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -422,3 +422,40 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------ */
+/*
+ * Accuracy yardstick (NOT a reference output): the same formulas as orc_cf in
+ * x87 long double (64-bit mantissa).  Used by tests/test_conditioning.py to
+ * measure how far the reference's own double-precision result is from the
+ * mathematically exact value where the little-trap form is ill-conditioned
+ * (small sigma: kappa*theta/sigma^2 up to 1e5 inside the calibrator's bounds).
+ */
+void orc_cf_ld(const double *p, double ur, double ui, double T, double S0, double r, double q,
+               double *out) {
+    typedef long double complex lc;
+    const long double kappa = p[0], theta = p[1], sigma = p[2], rho = p[3], v0 = p[4];
+    const lc u = (long double)ur + (long double)ui * I;
+    const lc i = I;
+    const lc s2 = sigma * sigma;
+    lc phi;
+    if (T <= 0.0) {
+        phi = cexpl(i * u * logl((long double)S0));
+    } else {
+        lc xi = kappa - rho * sigma * i * u;
+        lc d = csqrtl(xi * xi + s2 * (i * u + u * u));
+        lc g = (xi - d) / (xi + d);
+        lc e = cexpl(-d * (long double)T);
+        lc Cc = (kappa * theta / s2) * ((xi - d) * (long double)T - 2.0L * clogl((1.0L - g * e) / (1.0L - g)));
+        lc D = ((xi - d) / s2) * ((1.0L - e) / (1.0L - g * e));
+        phi = cexpl(Cc + D * v0 + i * u * logl((long double)S0) +
+                    ((long double)r - (long double)q) * i * u * (long double)T);
+    }
+    out[0] = (double)creall(phi);
+    out[1] = (double)cimagl(phi);
+}
+
+void orc_cf_ld_grid(const double *p, int n, const double *ur, double ui, double T, double S0, double r,
+                    double q, double *out) {
+    for (int j = 0; j < n; ++j) orc_cf_ld(p, ur[j], ui, T, S0, r, q, out + 2 * (size_t)j);
+}

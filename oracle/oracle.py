@@ -79,6 +79,15 @@ class Oracle:
                              out.ctypes.data_as(_dp))
         return out[..., 0] + 1j * out[..., 1]
 
+    def cf_ld_grid(self, p, T, ur, ui, S0, r, q) -> np.ndarray:
+        """Long-double yardstick (NOT a reference output): complex128[n_u]."""
+        p_, pp = _d(p)
+        ur, up = _d(ur)
+        out = np.empty((ur.size, 2))
+        self.lib.orc_cf_ld_grid(pp, C.c_int(ur.size), up, C.c_double(ui), C.c_double(T), C.c_double(S0),
+                                C.c_double(r), C.c_double(q), out.ctypes.data_as(_dp))
+        return out[:, 0] + 1j * out[:, 1]
+
     def price_refgrid(self, p, K, T, S0, r, q, is_call=True) -> float:
         p_, pp = _d(p)
         return float(self.lib.orc_price_refgrid(pp, K, T, S0, r, q, int(bool(is_call))))

@@ -1,0 +1,644 @@
+// heston_b200.cu -- C ABI (include/heston_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// Host side only does what the reference's binding layer does around the hot path
+// (src/cpp/bindings/heston_bindings.cpp, src/cpp/models/heston.cpp:153-167, :220-245):
+// argument checks, error strings, grouping the flat option list by maturity, and launching.
+// There is no CPU pricing code here: without a CUDA device every compute call fails.
+#include "../../include/heston_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+using namespace hb;
+
+thread_local std::string g_err = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define HB_CUDA(expr)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            return fail(HB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+        }                                                                                                \
+    } while (0)
+
+constexpr double kPi = 3.14159265358979323846;  // heston.cpp:13
+
+// Device buffer (optionally with a pinned host mirror) that only ever grows.
+struct Arena {
+    void* dev = nullptr;
+    void* pinned = nullptr;
+    size_t cap = 0;
+    bool want_pinned = false;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return HB_OK;
+        size_t ncap = std::max<size_t>(bytes, cap * 2);
+        ncap = (ncap + 255) & ~size_t(255);
+        release();
+        HB_CUDA(cudaMalloc(&dev, ncap));
+        if (want_pinned) HB_CUDA(cudaHostAlloc(&pinned, ncap, cudaHostAllocDefault));
+        cap = ncap;
+        return HB_OK;
+    }
+    void release() {
+        if (dev) cudaFree(dev);
+        if (pinned) cudaFreeHost(pinned);
+        dev = pinned = nullptr;
+        cap = 0;
+    }
+};
+
+// Packs host arrays into one blob so a surface upload is a single H2D copy.
+struct BlobBuilder {
+    std::vector<unsigned char> bytes;
+    template <typename T>
+    size_t add(const std::vector<T>& v) {
+        size_t off = (bytes.size() + 15) & ~size_t(15);
+        bytes.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
+        if (!v.empty()) std::memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+        return off;
+    }
+};
+
+}  // namespace
+
+struct hb_plan {
+    int mode = HB_MODE_FFT;
+    int N = 4096;
+    int device = 0;
+    int sm_count = 0;
+    double eta = 0.25, alpha = 0.75;
+    bool has_surface = false, has_market = false;
+    SurfaceDev S{};
+    Bounds bd{};
+    Arena surf, scratch, io_in, io_out, io_out2;
+    int n_sorted = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int validate_params(const double* p) {
+    // HestonParameters::validate, heston.hpp:81-100 (std::to_string == "%f")
+    char buf[96];
+    auto msg = [&](const char* fmt, double v) {
+        std::snprintf(buf, sizeof buf, fmt, v);
+        return fail(HB_ERR_INVALID_PARAMETER, buf);
+    };
+    if (!(p[0] > 0.0)) return msg("Heston: kappa must be positive, got %f", p[0]);
+    if (!(p[1] > 0.0)) return msg("Heston: theta must be positive, got %f", p[1]);
+    if (!(p[2] > 0.0)) return msg("Heston: sigma must be positive, got %f", p[2]);
+    if (!(std::fabs(p[3]) < 1.0)) return msg("Heston: |rho| must be < 1, got %f", p[3]);
+    if (!(p[4] > 0.0)) return msg("Heston: v0 must be positive, got %f", p[4]);
+    return HB_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return HB_OK;
+}
+
+int gmax_for(int N) { return (N == 4096 || N == 512) ? 3 : 1; }
+size_t fft_smem_bytes(int N, int g) { return (size_t)g * N * 16 + (size_t)(N / 8) * 16; }
+
+// Launch the pricing pipeline for P parameter sets (device SoA) and the requested output.
+int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, double* d_out, double* d_out2,
+                cudaStream_t st) {
+    if (!pl) return fail(HB_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (!pl->has_surface) return fail(HB_ERR_STATE, "hb_surface_set has not been called on this plan");
+    if (what != W_PRICE && !pl->has_market)
+        return fail(HB_ERR_STATE, "surface was set without market prices: only hb_price is available");
+    if (P < 0 || ld < P) return fail(HB_ERR_INVALID_ARGUMENT, "need 0 <= P <= ld");
+    if (P == 0) return HB_OK;
+    if (!d_params || !d_out || (what == W_JAC && !d_out2)) return fail(HB_ERR_INVALID_ARGUMENT, "NULL device pointer");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    const SurfaceDev& S = pl->S;
+    const int n = S.n_opt, M = S.n_mat, V = (what >= W_NEQ) ? 6 : 1;
+    GridConst gc = {pl->eta, pl->alpha, -(pl->alpha + 1.0), pl->eta / 3.0};
+    const size_t row_bytes = (size_t)6 * std::max(n, 1) * sizeof(double);
+
+    if (pl->mode == HB_MODE_FFT) {
+        const int gmax = gmax_for(pl->N);
+        const int g0 = ((V > 1 ? 3 * M : M) + gmax - 1) / gmax, g1 = (M + gmax - 1) / gmax;
+        const int groups = g0 + (V > 1 ? 3 : 0) * g1;
+        const int max_ctas = pl->sm_count;
+        // small batches: one job per (set, group) so every SM has work
+        const bool split = groups > 0 && (long long)P < 2LL * max_ctas && (size_t)P * row_bytes <= (size_t(1) << 30);
+        const long long n_jobs = split ? (long long)P * groups : (long long)P;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(n_jobs, max_ctas));
+        double* scratch = nullptr;
+        if (what != W_PRICE) {
+            int rc = pl->scratch.reserve((size_t)(split ? P : grid) * row_bytes);
+            if (rc) return rc;
+            scratch = (double*)pl->scratch.dev;
+        }
+        const size_t smem = fft_smem_bytes(pl->N, gmax);
+        if (pl->N == 4096) {
+            fft_job_kernel<4096, 512><<<grid, 512, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
+                                                              scratch, gmax, split ? 1 : 0);
+        } else {
+            fft_job_kernel<512, 128><<<grid, 128, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
+                                                             scratch, gmax, split ? 1 : 0);
+        }
+        g_launches++;
+        HB_CUDA(cudaGetLastError());
+        if (split && what != W_PRICE) {
+            finalize_rows_kernel<256><<<std::min(P, 4 * max_ctas), 256, 0, st>>>(S, pl->bd, d_params, ld, P, what,
+                                                                                  scratch, d_out, d_out2);
+            g_launches++;
+            HB_CUDA(cudaGetLastError());
+        }
+        return HB_OK;
+    }
+    // REFGRID
+    {
+        const int max_ctas = 2 * pl->sm_count;
+        const int slices = V * M;
+        const bool split = slices > 0 && (long long)P < 2LL * max_ctas && (size_t)P * row_bytes <= (size_t(1) << 30);
+        const long long n_jobs = split ? (long long)P * slices : (long long)P;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(n_jobs, max_ctas));
+        double* scratch = nullptr;
+        if (what != W_PRICE) {
+            int rc = pl->scratch.reserve((size_t)(split ? P : grid) * row_bytes);
+            if (rc) return rc;
+            scratch = (double*)pl->scratch.dev;
+        }
+        refgrid_job_kernel<256><<<grid, 256, 0, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch,
+                                                      split ? 1 : 0);
+        g_launches++;
+        HB_CUDA(cudaGetLastError());
+        if (split && what != W_PRICE) {
+            finalize_rows_kernel<256><<<std::min(P, 4 * pl->sm_count), 256, 0, st>>>(S, pl->bd, d_params, ld, P, what,
+                                                                                      scratch, d_out, d_out2);
+            g_launches++;
+            HB_CUDA(cudaGetLastError());
+        }
+        return HB_OK;
+    }
+}
+
+// Host-pointer path: AoS h_params[P][5] -> pinned SoA -> device -> kernels -> pinned -> user.
+int run_host(hb_plan* pl, const double* h_params, int P, int what, double* h_out, size_t out_elems, double* h_out2,
+             size_t out2_elems) {
+    if (!pl) return fail(HB_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (P < 0) return fail(HB_ERR_INVALID_ARGUMENT, "P must be >= 0");
+    if (P == 0) return HB_OK;
+    if (!h_params || !h_out || (out2_elems && !h_out2)) return fail(HB_ERR_INVALID_ARGUMENT, "NULL host pointer");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    pl->io_in.want_pinned = pl->io_out.want_pinned = pl->io_out2.want_pinned = true;
+    int rc;
+    if ((rc = pl->io_in.reserve((size_t)5 * P * sizeof(double)))) return rc;
+    if ((rc = pl->io_out.reserve(std::max<size_t>(out_elems, 1) * sizeof(double)))) return rc;
+    if (out2_elems && (rc = pl->io_out2.reserve(out2_elems * sizeof(double)))) return rc;
+    double* pin = (double*)pl->io_in.pinned;
+    for (int p = 0; p < P; ++p)
+        for (int c = 0; c < 5; ++c) pin[(size_t)c * P + p] = h_params[(size_t)p * 5 + c];
+    cudaStream_t st = 0;
+    HB_CUDA(cudaMemcpyAsync(pl->io_in.dev, pin, (size_t)5 * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = launch_jobs(pl, (const double*)pl->io_in.dev, P, P, what, (double*)pl->io_out.dev,
+                     out2_elems ? (double*)pl->io_out2.dev : nullptr, st);
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(pl->io_out.pinned, pl->io_out.dev, out_elems * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out2_elems)
+        HB_CUDA(cudaMemcpyAsync(pl->io_out2.pinned, pl->io_out2.dev, out2_elems * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(h_out, pl->io_out.pinned, out_elems * sizeof(double));
+    if (out2_elems) std::memcpy(h_out2, pl->io_out2.pinned, out2_elems * sizeof(double));
+    return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_version(void) { return 100; }
+const char* hb_last_error(void) { return g_err.c_str(); }
+uint64_t hb_launch_count(void) { return g_launches.load(); }
+
+int hb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, hb_plan** out) {
+    if (!out) return fail(HB_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (mode != HB_MODE_REFGRID && mode != HB_MODE_FFT) return fail(HB_ERR_INVALID_ARGUMENT, "unknown mode");
+    if (mode == HB_MODE_FFT) {
+        if (n_grid != 4096 && n_grid != 512)
+            return fail(HB_ERR_STATE, "FFT grid size must be 512 or 4096 (one slice per CTA's shared memory)");
+        if (!(eta > 0.0) || !(alpha > 0.0)) return fail(HB_ERR_INVALID_ARGUMENT, "eta and alpha must be positive");
+    } else {
+        if (alpha != 0.75) return fail(HB_ERR_INVALID_ARGUMENT, "refgrid mode is defined for alpha = 0.75 (heston.hpp:261)");
+        n_grid = kRefPoints;
+        eta = 0.01;
+    }
+    int ndev = hb_device_count();
+    if (ndev <= 0) return fail(HB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(HB_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(HB_ERR_CUDA, "this build targets sm_100a (B200) only");
+    hb_plan* pl = new hb_plan();
+    pl->mode = mode;
+    pl->N = n_grid;
+    pl->eta = eta;
+    pl->alpha = alpha;
+    pl->device = device;
+    pl->sm_count = prop.multiProcessorCount;
+    const double lb[5] = {0.1, 0.01, 0.01, -0.99, 0.01};  // heston_calibrator.py:201-207
+    const double ub[5] = {10.0, 1.0, 2.0, 0.99, 1.0};
+    std::memcpy(pl->bd.lb, lb, sizeof lb);
+    std::memcpy(pl->bd.ub, ub, sizeof ub);
+    if (mode == HB_MODE_FFT) {
+        int rc = (n_grid == 4096) ? set_smem(fft_job_kernel<4096, 512>, fft_smem_bytes(4096, gmax_for(4096)))
+                                  : set_smem(fft_job_kernel<512, 128>, fft_smem_bytes(512, gmax_for(512)));
+        if (rc) {
+            delete pl;
+            return rc;
+        }
+    }
+    *out = pl;
+    return HB_OK;
+}
+
+int hb_plan_destroy(hb_plan* pl) {
+    if (!pl) return HB_OK;
+    DeviceGuard guard(pl->device);
+    pl->surf.release();
+    pl->scratch.release();
+    pl->io_in.release();
+    pl->io_out.release();
+    pl->io_out2.release();
+    delete pl;
+    return HB_OK;
+}
+
+int hb_plan_n_options(const hb_plan* pl) { return pl && pl->has_surface ? pl->S.n_opt : 0; }
+int hb_plan_n_maturities(const hb_plan* pl) { return pl && pl->has_surface ? pl->S.n_mat : 0; }
+
+int hb_set_bounds(hb_plan* pl, const double* lb5, const double* ub5) {
+    if (!pl || !lb5 || !ub5) return fail(HB_ERR_INVALID_ARGUMENT, "NULL argument");
+    for (int c = 0; c < 5; ++c)
+        if (!(lb5[c] <= ub5[c])) return fail(HB_ERR_INVALID_ARGUMENT, "need lb <= ub");
+    std::memcpy(pl->bd.lb, lb5, 5 * sizeof(double));
+    std::memcpy(pl->bd.ub, ub5, 5 * sizeof(double));
+    return HB_OK;
+}
+
+int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* maturity, const uint8_t* is_call,
+                   const double* market, double spot, double rate, double dividend) {
+    if (!pl) return fail(HB_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (n_opt < 0 || (n_opt > 0 && (!strike || !maturity || !is_call)))
+        return fail(HB_ERR_INVALID_ARGUMENT, "NULL option arrays");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    const int N = pl->N;
+    const double alpha = pl->alpha, eta = pl->eta;
+    const double lambda = 2.0 * kPi / ((double)N * eta), b = kPi / eta;
+
+    // distinct maturities > 0 of valid options, ascending
+    std::vector<double> mats;
+    std::vector<int> intr_orig;
+    std::vector<double> intr_val;
+    for (int i = 0; i < n_opt; ++i) {
+        const double K = strike[i], T = maturity[i];
+        // price_option's checks, heston.cpp:156-164 (batched: NaN instead of throwing)
+        const bool bad = !(K > 0.0) || !(spot > 0.0) || !(T >= 0.0);
+        if (bad) {
+            intr_orig.push_back(i);
+            intr_val.push_back(nan);
+        } else if (T <= 0.0) {  // heston.cpp:97-100
+            intr_orig.push_back(i);
+            intr_val.push_back(is_call[i] ? std::max(spot - K, 0.0) : std::max(K - spot, 0.0));
+        } else {
+            mats.push_back(T);
+        }
+    }
+    std::sort(mats.begin(), mats.end());
+    mats.erase(std::unique(mats.begin(), mats.end()), mats.end());
+    const int M = (int)mats.size();
+    std::vector<std::vector<int>> by_mat(M);
+    for (int i = 0; i < n_opt; ++i) {
+        const double K = strike[i], T = maturity[i];
+        if (!(K > 0.0) || !(spot > 0.0) || !(T > 0.0)) continue;
+        int m = (int)(std::lower_bound(mats.begin(), mats.end(), T) - mats.begin());
+        by_mat[m].push_back(i);
+    }
+    std::vector<double> mat_disc(M), mat_fwd(M);
+    std::vector<int> mat_off(M + 1, 0), opt_orig, opt_bin, need_off(M + 1, 0), need_q;
+    std::vector<double> opt_frac, opt_s0, opt_s1, opt_lnk, opt_kdisc;
+    std::vector<uint8_t> opt_call;
+    const int NB = std::max(N / 8, 1);
+    for (int m = 0; m < M; ++m) {
+        const double T = mats[m];
+        const double disc = std::exp(-rate * T);  // heston.cpp:106
+        mat_disc[m] = disc;
+        mat_fwd[m] = spot * std::exp(-dividend * T);  // heston.cpp:148
+        std::vector<int> qs;
+        for (int i : by_mat[m]) {
+            const double K = strike[i], k = std::log(K);
+            opt_orig.push_back(i);
+            opt_lnk.push_back(k);
+            opt_kdisc.push_back(K * disc);
+            opt_call.push_back(is_call[i] ? 1 : 0);
+            if (pl->mode == HB_MODE_FFT) {
+                // SURVEY.md Appendix B step 6
+                const double fm = std::floor((k + b) / lambda);
+                if (!(fm >= 0.0) || !(fm < (double)(N - 1))) {
+                    opt_bin.push_back(-1);
+                    opt_frac.push_back(0.0);
+                    opt_s0.push_back(0.0);
+                    opt_s1.push_back(0.0);
+                } else {
+                    const int mm = (int)fm;
+                    const double km = -b + lambda * (double)mm, km1 = -b + lambda * (double)(mm + 1);
+                    opt_bin.push_back(mm);
+                    opt_frac.push_back((k - km) / lambda);
+                    opt_s0.push_back(std::exp(-alpha * km) / kPi);
+                    opt_s1.push_back(std::exp(-alpha * km1) / kPi);
+                    qs.push_back(mm % NB);
+                    qs.push_back((mm + 1) % NB);
+                }
+            } else {
+                opt_bin.push_back(0);
+                opt_frac.push_back(0.0);
+                opt_s0.push_back(std::exp(-alpha * k) / kPi);  // heston.cpp:139
+                opt_s1.push_back(0.0);
+            }
+        }
+        std::sort(qs.begin(), qs.end());
+        qs.erase(std::unique(qs.begin(), qs.end()), qs.end());
+        need_q.insert(need_q.end(), qs.begin(), qs.end());
+        need_off[m + 1] = (int)need_q.size();
+        mat_off[m + 1] = (int)opt_orig.size();
+    }
+    std::vector<double> mkt(n_opt, nan);
+    if (market) std::copy(market, market + n_opt, mkt.begin());
+
+    BlobBuilder bb;
+    const size_t o_T = bb.add(mats), o_disc = bb.add(mat_disc), o_fwd = bb.add(mat_fwd), o_moff = bb.add(mat_off),
+                 o_orig = bb.add(opt_orig), o_bin = bb.add(opt_bin), o_frac = bb.add(opt_frac), o_s0 = bb.add(opt_s0),
+                 o_s1 = bb.add(opt_s1), o_lnk = bb.add(opt_lnk), o_kd = bb.add(opt_kdisc), o_call = bb.add(opt_call),
+                 o_noff = bb.add(need_off), o_nq = bb.add(need_q), o_io = bb.add(intr_orig), o_iv = bb.add(intr_val),
+                 o_mkt = bb.add(mkt);
+    pl->surf.want_pinned = true;
+    int rc = pl->surf.reserve(bb.bytes.size());
+    if (rc) return rc;
+    std::memcpy(pl->surf.pinned, bb.bytes.data(), bb.bytes.size());
+    HB_CUDA(cudaMemcpyAsync(pl->surf.dev, pl->surf.pinned, bb.bytes.size(), cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    const unsigned char* base = (const unsigned char*)pl->surf.dev;
+    SurfaceDev& S = pl->S;
+    S.n_opt = n_opt;
+    S.n_mat = M;
+    S.n_intr = (int)intr_orig.size();
+    S.spot = spot;
+    S.rate = rate;
+    S.dividend = dividend;
+    S.ln_spot = std::log(spot);  // heston.cpp:91
+    S.mat_T = (const double*)(base + o_T);
+    S.mat_disc = (const double*)(base + o_disc);
+    S.mat_fwd = (const double*)(base + o_fwd);
+    S.mat_off = (const int*)(base + o_moff);
+    S.opt_orig = (const int*)(base + o_orig);
+    S.opt_bin = (const int*)(base + o_bin);
+    S.opt_frac = (const double*)(base + o_frac);
+    S.opt_s0 = (const double*)(base + o_s0);
+    S.opt_s1 = (const double*)(base + o_s1);
+    S.opt_lnk = (const double*)(base + o_lnk);
+    S.opt_kdisc = (const double*)(base + o_kd);
+    S.opt_call = (const uint8_t*)(base + o_call);
+    S.need_off = (const int*)(base + o_noff);
+    S.need_q = (const int*)(base + o_nq);
+    S.intr_orig = (const int*)(base + o_io);
+    S.intr_val = (const double*)(base + o_iv);
+    S.mkt_orig = (const double*)(base + o_mkt);
+    pl->n_sorted = (int)opt_orig.size();
+    pl->has_surface = true;
+    pl->has_market = market != nullptr;
+    return HB_OK;
+}
+
+int hb_price(hb_plan* pl, const double* d_params, int ld, int P, double* d_prices, void* stream) {
+    return launch_jobs(pl, d_params, ld, P, W_PRICE, d_prices, nullptr, (cudaStream_t)stream);
+}
+int hb_objective(hb_plan* pl, const double* d_params, int ld, int P, double* d_loss, void* stream) {
+    return launch_jobs(pl, d_params, ld, P, W_LOSS, d_loss, nullptr, (cudaStream_t)stream);
+}
+int hb_normal_eq(hb_plan* pl, const double* d_params, int ld, int P, double* d_out, void* stream) {
+    return launch_jobs(pl, d_params, ld, P, W_NEQ, d_out, nullptr, (cudaStream_t)stream);
+}
+int hb_jacobian(hb_plan* pl, const double* d_params, int ld, int P, double* d_res, double* d_jac, void* stream) {
+    return launch_jobs(pl, d_params, ld, P, W_JAC, d_res, d_jac, (cudaStream_t)stream);
+}
+
+int hb_cf(const double* d_params, int ld, int P, const double* d_T, int n_T, const double* d_ur, const double* d_ui,
+          int n_u, double spot, double rate, double dividend, double* d_out, void* stream) {
+    if (P < 0 || n_T < 0 || n_u < 0 || ld < P) return fail(HB_ERR_INVALID_ARGUMENT, "bad sizes");
+    const size_t total = (size_t)P * n_T * n_u;
+    if (total == 0) return HB_OK;
+    if (!d_params || !d_T || !d_ur || !d_ui || !d_out) return fail(HB_ERR_INVALID_ARGUMENT, "NULL device pointer");
+    const int block = 128;
+    const int grid = (int)std::min<size_t>((total + block - 1) / block, 148 * 32);
+    cf_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_params, ld, P, d_T, n_T, d_ur, d_ui, n_u, spot, rate,
+                                                        dividend, (double2*)d_out);
+    g_launches++;
+    HB_CUDA(cudaGetLastError());
+    return HB_OK;
+}
+
+int hb_fft_batch(double* d_data, int n, int n_slices, void* stream) {
+    if (n != 4096 && n != 512) return fail(HB_ERR_STATE, "FFT length must be 512 or 4096");
+    if (n_slices < 0) return fail(HB_ERR_INVALID_ARGUMENT, "n_slices < 0");
+    if (n_slices == 0) return HB_OK;
+    if (!d_data) return fail(HB_ERR_INVALID_ARGUMENT, "NULL device pointer");
+    int dev = 0, sms = 148;
+    HB_CUDA(cudaGetDevice(&dev));
+    HB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    constexpr int STAGES = 3;
+    const size_t smem = fft_smem_bytes(n, STAGES);
+    if (n == 4096) {
+        static int rc4096 = set_smem(fft_batch_kernel<4096, 512, STAGES>, fft_smem_bytes(4096, STAGES));
+        if (rc4096) return rc4096;
+        fft_batch_kernel<4096, 512, STAGES><<<std::min(n_slices, sms), 512, smem, (cudaStream_t)stream>>>(
+            (double2*)d_data, n_slices);
+    } else {
+        static int rc512 = set_smem(fft_batch_kernel<512, 64, STAGES>, fft_smem_bytes(512, STAGES));
+        if (rc512) return rc512;
+        fft_batch_kernel<512, 64, STAGES><<<std::min(n_slices, 4 * sms), 64, smem, (cudaStream_t)stream>>>(
+            (double2*)d_data, n_slices);
+    }
+    g_launches++;
+    HB_CUDA(cudaGetLastError());
+    return HB_OK;
+}
+
+int hb_sync(void* stream) {
+    HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return HB_OK;
+}
+
+int hb_price_host(hb_plan* pl, const double* h_params, int P, double* h_prices) {
+    const size_t n = pl && pl->has_surface ? (size_t)pl->S.n_opt : 0;
+    return run_host(pl, h_params, P, W_PRICE, h_prices, (size_t)P * n, nullptr, 0);
+}
+int hb_objective_host(hb_plan* pl, const double* h_params, int P, double* h_loss) {
+    return run_host(pl, h_params, P, W_LOSS, h_loss, (size_t)P, nullptr, 0);
+}
+int hb_normal_eq_host(hb_plan* pl, const double* h_params, int P, double* h_out) {
+    return run_host(pl, h_params, P, W_NEQ, h_out, (size_t)P * HB_NEQ_WIDTH, nullptr, 0);
+}
+int hb_jacobian_host(hb_plan* pl, const double* h_params, int P, double* h_res, double* h_jac) {
+    const size_t n = pl && pl->has_surface ? (size_t)pl->S.n_opt : 0;
+    return run_host(pl, h_params, P, W_JAC, h_res, (size_t)P * n, h_jac, (size_t)P * n * 5);
+}
+
+int hb_model_validate(const double* p) {
+    if (!p) return fail(HB_ERR_INVALID_ARGUMENT, "params is NULL");
+    return validate_params(p);
+}
+
+// One cached refgrid plan per (thread, device) keeps scalar calls at a few driver calls each.
+static hb_plan* scalar_plan(int device, int* rc) {
+    thread_local std::map<int, hb_plan*> cache;
+    auto it = cache.find(device);
+    if (it != cache.end()) {
+        *rc = HB_OK;
+        return it->second;
+    }
+    hb_plan* pl = nullptr;
+    *rc = hb_plan_create(HB_MODE_REFGRID, 0, 0.0, 0.75, device, &pl);
+    if (*rc == HB_OK) cache[device] = pl;
+    return pl;
+}
+
+int hb_model_cf(const double* p, double u_re, double u_im, double T, double spot, double rate, double dividend,
+                double* out2, int device) {
+    if (!p || !out2) return fail(HB_ERR_INVALID_ARGUMENT, "NULL argument");
+    int rc = validate_params(p);
+    if (rc) return rc;
+    hb_plan* pl = scalar_plan(device, &rc);
+    if (rc) return rc;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    pl->io_in.want_pinned = pl->io_out.want_pinned = true;
+    if ((rc = pl->io_in.reserve(8 * sizeof(double)))) return rc;
+    if ((rc = pl->io_out.reserve(2 * sizeof(double)))) return rc;
+    double* pin = (double*)pl->io_in.pinned;
+    for (int c = 0; c < 5; ++c) pin[c] = p[c];
+    pin[5] = T;
+    pin[6] = u_re;
+    pin[7] = u_im;
+    double* d = (double*)pl->io_in.dev;
+    HB_CUDA(cudaMemcpyAsync(d, pin, 8 * sizeof(double), cudaMemcpyHostToDevice, 0));
+    rc = hb_cf(d, 1, 1, d + 5, 1, d + 6, d + 7, 1, spot, rate, dividend, (double*)pl->io_out.dev, nullptr);
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(pl->io_out.pinned, pl->io_out.dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    out2[0] = ((double*)pl->io_out.pinned)[0];
+    out2[1] = ((double*)pl->io_out.pinned)[1];
+    return HB_OK;
+}
+
+int hb_model_price_options(const double* p, int n, const double* strikes, int n_maturity, const double* maturities,
+                           double spot, double rate, double dividend, int is_call, double* out, int device) {
+    if (!p) return fail(HB_ERR_INVALID_ARGUMENT, "params is NULL");
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (n < 0) return fail(HB_ERR_INVALID_ARGUMENT, "n < 0");
+    if (n == 0) return HB_OK;  // heston.cpp:224-226
+    if (!strikes || !maturities || !out) return fail(HB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_maturity != 1 && n_maturity != n)  // heston.cpp:228-231
+        return fail(HB_ERR_INVALID_ARGUMENT, "Maturities must have size 1 or match strikes size");
+    std::vector<double> T(n);
+    std::vector<uint8_t> ic(n, is_call ? 1 : 0);
+    for (int i = 0; i < n; ++i) {
+        T[i] = (n_maturity == 1) ? maturities[0] : maturities[i];
+        // price_option, heston.cpp:156-164
+        if (!(strikes[i] > 0.0)) return fail(HB_ERR_INVALID_ARGUMENT, "Strike must be positive");
+        if (!(spot > 0.0)) return fail(HB_ERR_INVALID_ARGUMENT, "Spot must be positive");
+        if (!(T[i] >= 0.0)) return fail(HB_ERR_INVALID_ARGUMENT, "Maturity must be non-negative");
+    }
+    hb_plan* pl = scalar_plan(device, &rc);
+    if (rc) return rc;
+    if ((rc = hb_surface_set(pl, n, strikes, T.data(), ic.data(), nullptr, spot, rate, dividend))) return rc;
+    return hb_price_host(pl, p, 1, out);
+}
+
+int hb_measure_fp64_peak(int device, double seconds, double* tflops) {
+    if (!tflops) return fail(HB_ERR_INVALID_ARGUMENT, "tflops is NULL");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    int sms = 0;
+    HB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int block = 256, grid = sms * 8;
+    double* d = nullptr;
+    HB_CUDA(cudaMalloc(&d, (size_t)grid * block * sizeof(double)));
+    cudaEvent_t e0, e1;
+    HB_CUDA(cudaEventCreate(&e0));
+    HB_CUDA(cudaEventCreate(&e1));
+    int iters = 2000;
+    double best = 0.0;
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::duration<double>(std::max(seconds, 0.05));
+    dfma_peak_kernel<<<grid, block>>>(d, iters, 1.0000001, 1e-9);  // warm-up
+    g_launches++;
+    do {
+        HB_CUDA(cudaEventRecord(e0));
+        dfma_peak_kernel<<<grid, block>>>(d, iters, 1.0000001, 1e-9);
+        g_launches++;
+        HB_CUDA(cudaEventRecord(e1));
+        HB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        HB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 16 * (double)iters * grid * block;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        if (ms < 20.f) iters *= 2;
+    } while (std::chrono::steady_clock::now() < t_end);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return HB_OK;
+}
+
+}  // extern "C"

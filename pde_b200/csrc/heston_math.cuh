@@ -1,0 +1,195 @@
+// heston_math.cuh -- FP64 real-arithmetic Heston characteristic function for sm_100a.
+//
+// Restates /root/reference src/cpp/models/heston.cpp:37-92
+// (compute_cf_intermediates + characteristic_function, the "little trap" form)
+// without std::complex, split into three stages so that work shared between the
+// slices of one calibration job is done once (SURVEY.md Appendix A "reuse"):
+//
+//   stage A  (kappa,sigma,rho ; u)        -> d, g, xi-d, g/(1-g)      T-independent
+//   stage B  (stage A ; T)                -> bracket B, Dq            theta/v0-independent
+//   stage F  (stage B ; theta, v0, T, ...) -> phi                      one cexp
+//
+//   C = (kappa*theta/sigma^2) * B,  B  = (xi-d) T - 2 log((1-g e)/(1-g))      heston.cpp:63-65
+//   D = Dq / sigma^2,               Dq = (xi-d) (1-e)/(1-g e)                 heston.cpp:69
+//   phi = exp(C + D v0 + i u (ln S0 + (r-q) T))                                heston.cpp:87-91
+//
+// Numerics.  The reference evaluates xi-d by subtraction and log(ratio) of a
+// ratio close to 1; both cancel when sigma is small (kappa*theta/sigma^2 up to
+// 1e5 inside the calibrator's bounds) and the reference's own double result is
+// only good to ~1e-10 there (tests/test_conditioning.py).  Here
+//   xi-d  = -sigma^2 (iu+u^2)/(xi+d)      (or xi+d from xi-d when Re xi < 0)
+//   log((1-g e)/(1-g)) = log1p-form of 1 + delta, delta = g (1-e)/(1-g)
+// so this side carries ~1e-15 relative error everywhere; branch choices
+// (principal csqrt with Re d >= 0, principal arg of the ratio) are the
+// reference's.
+//
+// Everything is `double`; the file also compiles as plain C++ (g++) so the
+// formulas can be checked on the CPU by tests/test_host_math.py -- that is a
+// test harness, never a product path.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define HB_HD __host__ __device__ __forceinline__
+#else
+#define HB_HD inline
+#endif
+
+namespace hb {
+
+struct cplx {
+    double re, im;
+};
+
+HB_HD cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+
+HB_HD double rsqrt_f64(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+HB_HD void sincos_f64(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+
+// Parameter-set constants shared by every grid point of a (kappa,sigma,rho) class.
+struct ClassConst {
+    double kappa, sigma2, rs;  // rs = rho*sigma
+};
+
+// T-independent stage, one per (class, u).
+struct StageA {
+    cplx d;    // principal sqrt, Re d >= 0                 heston.cpp:52
+    cplx g;    // (xi-d)/(xi+d)                             heston.cpp:56
+    cplx num;  // xi - d
+    cplx q1;   // g/(1-g) = (xi-d)/(2d)
+};
+
+HB_HD StageA stage_a(const ClassConst& c, double ur, double ui) {
+    StageA a;
+    // xi = kappa - rho sigma i u ; i u = (-ui, ur)
+    const double xr = c.kappa + c.rs * ui;
+    const double xi = -c.rs * ur;
+    // w = i u + u^2
+    const double wr = ur * ur - ui * ui - ui;
+    const double wi = 2.0 * ur * ui + ur;
+    const double swr = c.sigma2 * wr, swi = c.sigma2 * wi;
+    const double zr = xr * xr - xi * xi + swr;
+    const double zi = 2.0 * xr * xi + swi;
+    // d = csqrt(z), principal branch (glibc csqrt: Re >= 0, Im carries sign of zi)
+    const double m = sqrt(zr * zr + zi * zi);  // |z| = |d|^2
+    const double h = 0.5 * (m + fabs(zr));
+    const double rh = rsqrt_f64(h);
+    const double big = h * rh;           // sqrt(h)
+    const double small = 0.5 * zi * rh;  // zi / (2 sqrt(h)), signed
+    if (zr >= 0.0) {
+        a.d.re = big;
+        a.d.im = small;
+    } else {
+        a.d.re = fabs(small);
+        a.d.im = copysign(big, zi);
+    }
+    // xi -/+ d without cancellation: (xi-d)(xi+d) = xi^2 - d^2 = -sigma^2 w
+    cplx num, den;
+    if (xr >= 0.0) {
+        den = {xr + a.d.re, xi + a.d.im};
+        const double r = 1.0 / (den.re * den.re + den.im * den.im);
+        const cplx inv = {den.re * r, -den.im * r};
+        num = cmul({-swr, -swi}, inv);
+        a.g = cmul(num, inv);
+    } else {
+        num = {xr - a.d.re, xi - a.d.im};
+        const double r = 1.0 / (num.re * num.re + num.im * num.im);
+        const cplx inv = {num.re * r, -num.im * r};
+        den = cmul({-swr, -swi}, inv);
+        const double r2 = 1.0 / (den.re * den.re + den.im * den.im);
+        a.g = cmul(num, {den.re * r2, -den.im * r2});
+    }
+    a.num = num;
+    // q1 = num / (2 d) = num * conj(d) / (2 m)
+    const double rm = 0.5 / m;
+    a.q1 = cmul(num, {a.d.re * rm, -a.d.im * rm});
+    return a;
+}
+
+// theta/v0-independent stage, one per (stage A, T).
+struct StageB {
+    cplx B;   // (xi-d) T - 2 log((1 - g e)/(1 - g))
+    cplx Dq;  // (xi-d) (1-e)/(1-g e)
+};
+
+HB_HD StageB stage_b(const StageA& a, double T) {
+    StageB b;
+    // e = exp(-d T)                                          heston.cpp:59
+    const double ea = exp(-a.d.re * T);
+    double sn, cs;
+    sincos_f64(-a.d.im * T, &sn, &cs);
+    const cplx e = {ea * cs, ea * sn};
+    const cplx ome = {1.0 - e.re, -e.im};  // 1 - e
+    // ratio = (1-g e)/(1-g) = 1 + delta, delta = g (1-e)/(1-g)
+    const cplx dl = cmul(a.q1, ome);
+    const double x = 2.0 * dl.re + (dl.re * dl.re + dl.im * dl.im);  // |ratio|^2 - 1
+    const double lg = log1p(x);                                      // 2 Re log(ratio)
+    const double ar = atan2(dl.im, 1.0 + dl.re);                     // principal arg, as clog
+    b.B.re = a.num.re * T - lg;
+    b.B.im = a.num.im * T - 2.0 * ar;
+    // Dq = num (1-e)/(1-g e)
+    const cplx ge = cmul(a.g, e);
+    const cplx n = {1.0 - ge.re, -ge.im};
+    const double rn = 1.0 / (n.re * n.re + n.im * n.im);
+    const cplx Q = cmul(ome, {n.re * rn, -n.im * rn});
+    b.Dq = cmul(a.num, Q);
+    return b;
+}
+
+// Per-slice constants of stage F.
+struct SliceConst {
+    double kts;   // kappa*theta/sigma^2
+    double v0s;   // v0/sigma^2
+    double lsm;   // ln S0 + (r-q) T
+};
+
+// phi = exp(C + D v0 + i u (ln S0 + (r-q)T)),  i u = (-ui, ur)        heston.cpp:87-91
+HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui) {
+    const double er = s.kts * b.B.re + s.v0s * b.Dq.re - ui * s.lsm;
+    const double ei = s.kts * b.B.im + s.v0s * b.Dq.im + ur * s.lsm;
+    const double mag = exp(er);
+    double sn, cs;
+    sincos_f64(ei, &sn, &cs);
+    return {mag * cs, mag * sn};
+}
+
+// Full CF for arbitrary complex u (the bound API characteristic_function(u,T,S0,r,q)).
+HB_HD cplx heston_cf(double kappa, double theta, double sigma, double rho, double v0, double ur, double ui,
+                     double T, double S0, double r, double q) {
+    const double L = log(S0);
+    if (T <= 0.0) {  // heston.cpp:77-79: exp(i u ln S0)
+        const double mag = exp(-ui * L);
+        double sn, cs;
+        sincos_f64(ur * L, &sn, &cs);
+        return {mag * cs, mag * sn};
+    }
+    ClassConst c = {kappa, sigma * sigma, rho * sigma};
+    StageA a = stage_a(c, ur, ui);
+    StageB b = stage_b(a, T);
+    SliceConst s = {kappa * theta / c.sigma2, v0 / c.sigma2, L + (r - q) * T};
+    return stage_f(b, s, ur, ui);
+}
+
+// Carr-Madan damping denominator 1/(alpha^2+alpha-v^2 + i(2 alpha+1) v)   heston.cpp:117
+HB_HD cplx cm_inv_denominator(double v, double alpha) {
+    const double a = alpha * alpha + alpha - v * v;
+    const double b = (2.0 * alpha + 1.0) * v;
+    const double r = 1.0 / (a * a + b * b);
+    return {a * r, -b * r};
+}
+
+}  // namespace hb

@@ -1,0 +1,637 @@
+// kernels.cuh -- sm_100a kernels of the batched Heston pricing / calibration-objective path.
+//
+//   fft_job_kernel      K1+K2+K3 fused: one CTA per parameter-set job; characteristic
+//                       function on the damped grid -> slices in shared memory -> in-place
+//                       Stockham FFT -> log-strike interpolation -> prices / loss /
+//                       finite-difference normal equations.  psi never touches HBM.
+//   refgrid_job_kernel  K1': the reference's own arithmetic (1023-point quadrature,
+//                       heston.cpp:94-151) as CF-once-per-slice + per-strike twiddle sums.
+//   cf_kernel           K1 alone: phi(u; T) for arbitrary complex u (heston.cpp:74-92).
+//   fft_batch_kernel    K2 alone: bulk-async (TMA) staged batched FFT, HBM -> smem -> HBM.
+//   dfma_peak_kernel    FP64-pipe roofline probe.
+//
+// Job = one base parameter set.  In normal-equation / Jacobian mode the job prices 6
+// variants (base + 5 forward-difference perturbations, SciPy step rule)
+// and shares work between them:
+//   class 0 = {base, theta+h, v0+h}: same (kappa,sigma,rho) => same stage A and stage B;
+//             only the final cexp differs -> the three slices of one maturity are one group.
+//   classes kappa+h, sigma+h, rho+h: own stage A, shared by the 3 maturities of a group.
+// A group = up to 3 slices that are resident in shared memory at once (3 x 64 KiB at
+// N = 4096).  Arithmetic of a perturbed slice is identical to evaluating it on its own.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_smem.cuh"
+#include "heston_math.cuh"
+
+namespace hb {
+
+enum What { W_PRICE = 0, W_LOSS = 1, W_NEQ = 2, W_JAC = 3 };
+
+// Device view of the option surface, grouped by distinct maturity (CSR).  "sorted" arrays
+// are in maturity-group order; opt_orig maps back to the caller's option index.
+struct SurfaceDev {
+    int n_opt, n_mat, n_intr;
+    double spot, rate, dividend, ln_spot;
+    const double* mat_T;     // [n_mat] distinct maturities > 0
+    const double* mat_disc;  // exp(-r T)
+    const double* mat_fwd;   // S0 exp(-q T)
+    const int* mat_off;      // [n_mat+1]
+    const int* opt_orig;     // [n_sorted]
+    const int* opt_bin;      // FFT: lower grid bin m, -1 if ln K is off the grid
+    const double* opt_frac;  // FFT: (k - k_m)/lambda
+    const double* opt_s0;    // FFT: exp(-alpha k_m)/pi        REFGRID: exp(-alpha ln K)/pi
+    const double* opt_s1;    // FFT: exp(-alpha k_{m+1})/pi
+    const double* opt_lnk;   // ln K
+    const double* opt_kdisc; // K exp(-r T) (put parity, heston.cpp:148)
+    const uint8_t* opt_call;
+    const int* need_off;     // [n_mat+1] pruned last-pass butterflies per maturity
+    const int* need_q;
+    const int* intr_orig;    // options not priced through a slice (T == 0 or invalid)
+    const double* intr_val;  // intrinsic value or NaN
+    const double* mkt_orig;  // [n_opt] market prices in caller order (may be null for W_PRICE)
+};
+
+struct GridConst {
+    double eta, alpha, ui, w0;  // ui = -(alpha+1), w0 = eta/3
+};
+
+struct Bounds {
+    double lb[5], ub[5];
+};
+
+constexpr int kMaxGroup = 3;
+
+struct SubSlice {
+    double T, kts, v0s, lsm, disc, fwd;
+    int mat, variant;
+};
+struct Group {
+    ClassConst cc;
+    int count;
+    SubSlice s[kMaxGroup];
+};
+
+// Variant v of the base set x: v = 0 base, v = 1..5 perturbs x[v-1].
+struct JobState {
+    double x[6][5];
+    double dx[5];
+    int valid;
+};
+
+// HestonParameters::is_valid, heston.hpp:72-74
+__device__ __forceinline__ bool params_valid(const double* x) {
+    return x[0] > 0.0 && x[1] > 0.0 && x[2] > 0.0 && fabs(x[3]) < 1.0 && x[4] > 0.0;
+}
+
+// SciPy 2-point step with bounds (scipy/optimize/_numdiff.py
+// _compute_absolute_step + _adjust_scheme_to_bounds '1-sided').
+__device__ __forceinline__ double fd_step(double x, double lb, double ub) {
+    const double rstep = 1.4901161193847656e-08;
+    double h = rstep * (x >= 0.0 ? 1.0 : -1.0) * fmax(1.0, fabs(x));
+    const double lower = x - lb, upper = ub - x;
+    const double xn = x + h;
+    const bool violated = (xn < lb) || (xn > ub);
+    const bool fitting = fabs(h) <= fmax(lower, upper);
+    if (violated && fitting) h = -h;
+    if (!fitting) h = (upper >= lower) ? upper : -lower;
+    return h;
+}
+
+__device__ __forceinline__ void job_setup(JobState& js, const double* params, int ld, int p, const Bounds& bd,
+                                          int V) {
+    double x[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) x[c] = params[(size_t)c * ld + p];
+    js.valid = params_valid(x);
+#pragma unroll
+    for (int v = 0; v < 6; ++v)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) js.x[v][c] = x[c];
+    if (V > 1) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const double h = fd_step(x[c], bd.lb[c], bd.ub[c]);
+            const double x1 = x[c] + h;
+            js.x[c + 1][c] = x1;
+            js.dx[c] = x1 - x[c];  // (x0 + h) - x0, as _dense_difference does
+        }
+    }
+}
+
+// Sub-slice list of a class.  In 6-variant mode class 0 enumerates (maturity, {base,
+// theta', v0'}) so that a group of 3 shares one maturity; other classes enumerate maturities.
+__device__ __forceinline__ void sub_slice_at(int cls, int V, int t, int& variant, int& mat) {
+    if (V > 1 && cls == 0) {
+        const int r = t % 3;
+        mat = t / 3;
+        variant = (r == 0) ? 0 : (r == 1 ? 2 : 5);
+    } else {
+        mat = t;
+        variant = cls;
+    }
+}
+
+__device__ __forceinline__ void fill_group(Group& grp, const JobState& js, const SurfaceDev& S, int cls, int V,
+                                           int t0, int n_total, int gmax) {
+    const double* xc = js.x[cls];
+    grp.cc.kappa = xc[0];
+    grp.cc.sigma2 = xc[2] * xc[2];
+    grp.cc.rs = xc[3] * xc[2];
+    const int cnt = min(gmax, n_total - t0);
+    grp.count = cnt;
+    for (int g = 0; g < cnt; ++g) {
+        int variant, mat;
+        sub_slice_at(cls, V, t0 + g, variant, mat);
+        const double* xv = js.x[variant];
+        SubSlice& s = grp.s[g];
+        s.variant = variant;
+        s.mat = mat;
+        s.T = S.mat_T[mat];
+        s.kts = xv[0] * xv[1] / grp.cc.sigma2;  // kappa*theta/sigma^2, heston.cpp:65
+        s.v0s = xv[4] / grp.cc.sigma2;
+        s.lsm = S.ln_spot + (S.rate - S.dividend) * s.T;
+        s.disc = S.mat_disc[mat];
+        s.fwd = S.mat_fwd[mat];
+    }
+}
+
+// ---- block reductions ---------------------------------------------------------------------
+
+template <int NT, int W>
+__device__ __forceinline__ void block_sum(double (&acc)[W], double* red /* [NT/32][W] */, int tid) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) red[warp * W + i] = acc[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            double v = (lane < NT / 32) ? red[lane * W + i] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[i] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// _compute_residuals, heston_calibrator.py:533-535 (np.maximum propagates NaN)
+__device__ __forceinline__ double residual_of(double price, double mkt) {
+    const double p = (price != price) ? price : fmax(price, 1e-10);
+    return (p - mkt) / mkt;
+}
+
+// Turn the price rows of one job into the requested output.  rows[v * n_opt + i].
+template <int NT>
+__device__ __forceinline__ void finalize_job(int what, const double* rows, const SurfaceDev& S, const JobState& js,
+                                             int p, double* out, double* out2, double* red, int tid) {
+    const int n = S.n_opt;
+    if (what == W_PRICE) return;
+    if (what == W_LOSS) {
+        double acc[2] = {0.0, 0.0};
+        for (int i = tid; i < n; i += NT) {
+            const double pr = rows[i], m = S.mkt_orig[i];
+            if (pr != pr || pr <= 0.0) {
+                acc[1] += 1.0;  // heston_calibrator.py:507-508
+            } else {
+                const double e = (pr - m) / m;
+                acc[0] += e * e;
+            }
+        }
+        block_sum<NT, 2>(acc, red, tid);
+        if (tid == 0) out[p] = (acc[1] > 0.0) ? 1e10 : acc[0];
+        return;
+    }
+    if (what == W_JAC) {
+        for (int i = tid; i < n; i += NT) {
+            const double m = S.mkt_orig[i];
+            const double r0 = residual_of(rows[i], m);
+            out[(size_t)p * n + i] = r0;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const double rc = residual_of(rows[(size_t)(c + 1) * n + i], m);
+                out2[((size_t)p * n + i) * 5 + c] = (rc - r0) / js.dx[c];
+            }
+        }
+        return;
+    }
+    // W_NEQ: { loss, ||r||^2, J^T r, triu(J^T J) }
+    double acc[23];
+#pragma unroll
+    for (int i = 0; i < 23; ++i) acc[i] = 0.0;
+    for (int i = tid; i < n; i += NT) {
+        const double pr = rows[i], m = S.mkt_orig[i];
+        if (pr != pr || pr <= 0.0) {
+            acc[22] += 1.0;
+        } else {
+            const double e = (pr - m) / m;
+            acc[0] += e * e;
+        }
+        const double r0 = residual_of(pr, m);
+        double J[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) J[c] = (residual_of(rows[(size_t)(c + 1) * n + i], m) - r0) / js.dx[c];
+        acc[1] += r0 * r0;
+        int t = 7;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            acc[2 + a] += J[a] * r0;
+#pragma unroll
+            for (int c = a; c < 5; ++c) acc[t++] += J[a] * J[c];
+        }
+    }
+    block_sum<NT, 23>(acc, red, tid);
+    if (tid == 0) {
+        double* o = out + (size_t)p * 22;
+        o[0] = (acc[22] > 0.0) ? 1e10 : acc[0];
+        for (int i = 1; i < 22; ++i) o[i] = acc[i];
+    }
+}
+
+// Outputs of a job whose base parameter set is invalid: NaN prices -> 1e10 loss.
+template <int NT>
+__device__ __forceinline__ void invalid_job(int what, const SurfaceDev& S, int p, double* out, double* out2,
+                                            int tid) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const int n = S.n_opt;
+    if (what == W_PRICE) {
+        for (int i = tid; i < n; i += NT) out[(size_t)p * n + i] = nan;
+    } else if (what == W_LOSS) {
+        if (tid == 0) out[p] = 1e10;
+    } else if (what == W_NEQ) {
+        if (tid < 22) out[(size_t)p * 22 + tid] = (tid == 0) ? 1e10 : nan;
+    } else {
+        for (int i = tid; i < n; i += NT) {
+            out[(size_t)p * n + i] = nan;
+            for (int c = 0; c < 5; ++c) out2[((size_t)p * n + i) * 5 + c] = nan;
+        }
+    }
+}
+
+// clamp + put-call parity of price_option_integration, heston.cpp:142-149.
+// std::max(x, 0.0) keeps a NaN x (x < 0 is false), unlike fmax.
+__device__ __forceinline__ double finish_price(double call, bool is_call, double fwd, double kdisc) {
+    call = (call < 0.0) ? 0.0 : call;
+    if (is_call) return call;
+    const double put = call - fwd + kdisc;
+    return (put < 0.0) ? 0.0 : put;
+}
+
+// ============================================================================================
+// Fused Carr-Madan FFT job kernel
+// ============================================================================================
+
+template <int N, int NT>
+__global__ void __launch_bounds__(NT, 1)
+fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
+               double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int gmax,
+               int split) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* slices = reinterpret_cast<double2*>(smem_raw);
+    double2* tw = slices + (size_t)gmax * N;
+    __shared__ Group grp;
+    __shared__ JobState js;
+    __shared__ double red[(NT / 32) * 23];
+    const int tid = threadIdx.x;
+    const int V = (what >= W_NEQ) ? 6 : 1;
+    const int n = S.n_opt, M = S.n_mat;
+    // groups of one parameter set: class 0 first, then kappa', sigma', rho' (6-variant mode)
+    const int n_cls = (V == 1) ? 1 : 4;
+    const int g0 = ((V > 1 ? 3 * M : M) + gmax - 1) / gmax;
+    const int g1 = (M + gmax - 1) / gmax;
+    const int groups_per_set = g0 + (n_cls - 1) * g1;
+    // split = one job per (set, group) with rows in global memory and a separate finalize
+    // kernel (small P: fills the SMs); otherwise one job per set, finalized in place.
+    const long long n_jobs = split ? (long long)P * groups_per_set : (long long)P;
+
+    fill_twiddles<N>(tw, tid, NT);
+
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int p = split ? (int)(job / groups_per_set) : (int)job;
+        const int gi_begin = split ? (int)(job % groups_per_set) : 0;
+        const int gi_end = split ? gi_begin + 1 : groups_per_set;
+        __syncthreads();  // previous job's finalize has consumed rows/js
+        if (tid == 0) job_setup(js, params, ld, p, bd, V);
+        __syncthreads();
+        if (!js.valid) {
+            if (!split) invalid_job<NT>(what, S, p, out, out2, tid);
+            else if (what == W_PRICE && gi_begin == 0) invalid_job<NT>(what, S, p, out, out2, tid);
+            continue;
+        }
+        double* rows = (what == W_PRICE) ? out + (size_t)p * n
+                                         : scratch + (size_t)(split ? p : (int)blockIdx.x) * 6 * n;
+        if (gi_begin == 0) {
+            for (int v = 0; v < V; ++v)
+                for (int i = tid; i < S.n_intr; i += NT) rows[(size_t)v * n + S.intr_orig[i]] = S.intr_val[i];
+        }
+        for (int gi = gi_begin; gi < gi_end; ++gi) {
+            const int ci = (gi < g0) ? 0 : 1 + (gi - g0) / g1;
+            const int cls = (ci == 0) ? 0 : (ci == 1 ? 1 : (ci == 2 ? 3 : 4));  // base | kappa' | sigma' | rho'
+            const int n_total = (V > 1 && cls == 0) ? 3 * M : M;
+            const int t0 = ((gi < g0) ? gi : (gi - g0) % g1) * gmax;
+            if (tid == 0) fill_group(grp, js, S, cls, V, t0, n_total, gmax);
+            __syncthreads();
+            const int count = grp.count;
+            // ---- K1: characteristic function on the damped grid -> x_j in shared memory ----
+            {
+                const ClassConst cc = grp.cc;
+#pragma unroll 1
+                for (int j = tid; j < N; j += NT) {
+                    const double v = gc.eta * (double)j;
+                    const StageA a = stage_a(cc, v, gc.ui);
+                    cplx tab = cm_inv_denominator(v, gc.alpha);
+                    // Simpson weight times e^{i b v_j} = (-1)^j   
+                    const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
+                    tab.re *= wgt;
+                    tab.im *= wgt;
+                    StageB b = {};
+                    double Tprev = -1.0;
+#pragma unroll 1
+                    for (int g = 0; g < count; ++g) {
+                        const SubSlice& s = grp.s[g];
+                        if (s.T != Tprev) {
+                            b = stage_b(a, s.T);
+                            Tprev = s.T;
+                        }
+                        const SliceConst sc = {s.kts, s.v0s, s.lsm};
+                        const cplx phi = stage_f(b, sc, v, gc.ui);
+                        sts_c(slices + (size_t)g * N, j, cmul(phi, tab));
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- K2: Stockham FFT in shared memory, last pass pruned to the quoted bins ----
+            for (int Ns = 1; Ns < N / 8; Ns *= 8) fft_pass<N, NT>(slices, count, gmax, tw, Ns, tid);
+            __syncthreads();
+            for (int g = 0; g < count; ++g) {
+                const int mat = grp.s[g].mat;
+                const int q0 = S.need_off[mat];
+                fft_last_pass_pruned<N, NT>(slices + (size_t)g * N, tw, S.need_q + q0, S.need_off[mat + 1] - q0, tid);
+            }
+            __syncthreads();
+            // ---- K3: log-strike interpolation, clamp, parity -> price rows ----
+            for (int g = 0; g < count; ++g) {
+                const SubSlice& s = grp.s[g];
+                const double2* sl = slices + (size_t)g * N;
+                const int o1 = S.mat_off[s.mat + 1];
+                for (int o = S.mat_off[s.mat] + tid; o < o1; o += NT) {
+                    const int bin = S.opt_bin[o];
+                    double price = __longlong_as_double(0x7ff8000000000000LL);
+                    if (bin >= 0) {
+                        const double c0 = S.opt_s0[o] * sl[swz(bin)].x;
+                        const double c1 = S.opt_s1[o] * sl[swz(bin + 1)].x;
+                        const double call = s.disc * (c0 + (c1 - c0) * S.opt_frac[o]);
+                        price = finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]);
+                    }
+                    rows[(size_t)s.variant * n + S.opt_orig[o]] = price;
+                }
+            }
+            __syncthreads();  // slices and grp are free again
+        }
+        if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
+    }
+}
+
+// Finalize for split launches: one CTA per parameter set, rows[p][6][n_opt] in global memory.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+finalize_rows_kernel(SurfaceDev S, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
+                     const double* __restrict__ rows_buf, double* __restrict__ out, double* __restrict__ out2) {
+    __shared__ JobState js;
+    __shared__ double red[(NT / 32) * 23];
+    const int tid = threadIdx.x;
+    const int V = (what >= W_NEQ) ? 6 : 1;
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) job_setup(js, params, ld, p, bd, V);
+        __syncthreads();
+        if (!js.valid) {
+            invalid_job<NT>(what, S, p, out, out2, tid);
+            continue;
+        }
+        finalize_job<NT>(what, rows_buf + (size_t)p * 6 * S.n_opt, S, js, p, out, out2, red, tid);
+    }
+}
+
+// ============================================================================================
+// Reference-grid ("refgrid") job kernel: heston.cpp:94-151 restated as
+//   psi_j = phi(v_j - 1.75 i)/(alpha^2+alpha-v_j^2 + i(2 alpha+1)v_j), v_j = 0.01 j, j=1..1023
+//   call  = e^{-alpha ln K}/pi * e^{-rT} * 0.01 * sum_j Re(e^{-i v_j ln K} psi_j)
+// The CF is evaluated once per slice instead of once per (strike, j).
+// ============================================================================================
+
+constexpr int kRefPoints = 1024;  // heston.cpp:126
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
+refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
+                   double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int split) {
+    __shared__ double2 psi[kRefPoints];
+    __shared__ JobState js;
+    __shared__ double red[(NT / 32) * 23];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int V = (what >= W_NEQ) ? 6 : 1;
+    const int n = S.n_opt, M = S.n_mat;
+    const double du = 0.01;  // heston.cpp:127
+    const int slices_per_set = V * M;
+    const long long n_jobs = split ? (long long)P * slices_per_set : (long long)P;
+
+    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int p = split ? (int)(job / slices_per_set) : (int)job;
+        const int si_begin = split ? (int)(job % slices_per_set) : 0;
+        const int si_end = split ? si_begin + 1 : slices_per_set;
+        __syncthreads();
+        if (tid == 0) job_setup(js, params, ld, p, bd, V);
+        __syncthreads();
+        if (!js.valid) {
+            if (!split) invalid_job<NT>(what, S, p, out, out2, tid);
+            else if (what == W_PRICE && si_begin == 0) invalid_job<NT>(what, S, p, out, out2, tid);
+            continue;
+        }
+        double* rows = (what == W_PRICE) ? out + (size_t)p * n
+                                         : scratch + (size_t)(split ? p : (int)blockIdx.x) * 6 * n;
+        if (si_begin == 0) {
+            for (int v = 0; v < V; ++v)
+                for (int i = tid; i < S.n_intr; i += NT) rows[(size_t)v * n + S.intr_orig[i]] = S.intr_val[i];
+        }
+        for (int si = si_begin; si < si_end; ++si) {
+            const int vnt = si / M, mat = si % M;
+            const double* x = js.x[vnt];
+            const ClassConst cc = {x[0], x[2] * x[2], x[3] * x[2]};
+            const double T = S.mat_T[mat];
+            const SliceConst sc = {x[0] * x[1] / cc.sigma2, x[4] / cc.sigma2, S.ln_spot + (S.rate - S.dividend) * T};
+#pragma unroll 1
+            for (int j = tid; j < kRefPoints; j += NT) {
+                cplx r = {0.0, 0.0};  // integrand(0) == 0, heston.cpp:110
+                if (j > 0) {
+                    const double v = (double)j * du;
+                    const StageA a = stage_a(cc, v, gc.ui);
+                    const StageB b = stage_b(a, T);
+                    r = cmul(stage_f(b, sc, v, gc.ui), cm_inv_denominator(v, gc.alpha));
+                }
+                psi[j] = make_double2(r.re, r.im);
+            }
+            __syncthreads();
+            const double disc = S.mat_disc[mat], fwd = S.mat_fwd[mat];
+            const int o1 = S.mat_off[mat + 1];
+            for (int o = S.mat_off[mat] + warp; o < o1; o += NT / 32) {
+                const double k = S.opt_lnk[o];
+                // e^{-i v_j k}, j = lane + 32 a: base rotation times a 32-step recurrence
+                double sb, cb, ss, cs;
+                sincos(-((double)lane * du) * k, &sb, &cb);
+                sincos(-(32.0 * du) * k, &ss, &cs);
+                cplx twd = {cb, sb};
+                const cplx st = {cs, ss};
+                double sum = 0.0;
+#pragma unroll 4
+                for (int a = 0; a < kRefPoints / 32; ++a) {
+                    const double2 ps = psi[lane + 32 * a];
+                    sum += twd.re * ps.x - twd.im * ps.y;
+                    twd = cmul(twd, st);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                if (lane == 0) {
+                    const double call = S.opt_s0[o] * disc * (sum * du);  // heston.cpp:136-139
+                    rows[(size_t)vnt * n + S.opt_orig[o]] = finish_price(call, S.opt_call[o] != 0, fwd, S.opt_kdisc[o]);
+                }
+            }
+            __syncthreads();
+        }
+        if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
+    }
+}
+
+// ============================================================================================
+// K1 alone: characteristic function for arbitrary complex u
+// ============================================================================================
+
+__global__ void cf_kernel(const double* __restrict__ params, int ld, int P, const double* __restrict__ T, int n_T,
+                          const double* __restrict__ ur, const double* __restrict__ ui, int n_u, double spot,
+                          double rate, double dividend, double2* __restrict__ out) {
+    const size_t total = (size_t)P * n_T * n_u;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % n_u);
+        const size_t pm = idx / n_u;
+        const int m = (int)(pm % n_T);
+        const int p = (int)(pm / n_T);
+        const cplx z = heston_cf(params[p], params[(size_t)ld + p], params[(size_t)2 * ld + p],
+                                 params[(size_t)3 * ld + p], params[(size_t)4 * ld + p], ur[j], ui[j], T[m], spot,
+                                 rate, dividend);
+        out[idx] = make_double2(z.re, z.im);
+    }
+}
+
+// ============================================================================================
+// K2 alone: batched FFT, slices staged HBM -> shared memory with cp.async.bulk (TMA engine,
+// SASS UBLKCP) behind an mbarrier, 3-deep ring so the copy of slice s+2 overlaps the
+// transform of slice s.
+// ============================================================================================
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int N, int NT, int STAGES>
+__global__ void __launch_bounds__(NT, 1) fft_batch_kernel(double2* __restrict__ data, int n_slices) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* bufs = reinterpret_cast<double2*>(smem_raw);
+    double2* tw = bufs + (size_t)STAGES * N;
+    __shared__ __align__(8) uint64_t bar[STAGES];
+    const int tid = threadIdx.x;
+    constexpr uint32_t kBytes = (uint32_t)N * sizeof(double2);
+
+    fill_twiddles<N>(tw, tid, NT);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n_mine = (first < n_slices) ? (n_slices - first + stride - 1) / stride : 0;
+    if (tid == 0) {
+        for (int it = 0; it < STAGES - 1 && it < n_mine; ++it) {
+            mbar_expect_tx(&bar[it], kBytes);
+            bulk_g2s(bufs + (size_t)it * N, data + (size_t)(first + it * stride) * N, kBytes, &bar[it]);
+        }
+    }
+    for (int it = 0; it < n_mine; ++it) {
+        const int st = it % STAGES;
+        // refill the stage consumed in the previous iteration with slice it + STAGES - 1
+        if (tid == 0 && it + STAGES - 1 < n_mine) {
+            const int nx = (it + STAGES - 1) % STAGES;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar[nx], kBytes);
+            bulk_g2s(bufs + (size_t)nx * N, data + (size_t)(first + (it + STAGES - 1) * stride) * N, kBytes,
+                     &bar[nx]);
+        }
+        mbar_wait(&bar[st], (uint32_t)((it / STAGES) & 1));
+        double2* buf = bufs + (size_t)st * N;
+        fft_pass<N, NT, true>(buf, 1, 1, tw, 1, tid);
+        for (int Ns = 8; Ns < N; Ns *= 8) fft_pass<N, NT, false>(buf, 1, 1, tw, Ns, tid);
+        double2* dst = data + (size_t)(first + it * stride) * N;
+        for (int i = tid; i < N; i += NT) dst[i] = buf[swz(i)];
+        __syncthreads();  // stage st fully read before it is refilled next iteration
+    }
+}
+
+// ============================================================================================
+// FP64 pipe probe: 8 independent DFMA chains per thread
+// ============================================================================================
+
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace hb

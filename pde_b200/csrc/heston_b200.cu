@@ -139,6 +139,7 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
         return fail(HB_ERR_STATE, "surface was set without market prices: only hb_price is available");
     if (P < 0 || ld < P) return fail(HB_ERR_INVALID_ARGUMENT, "need 0 <= P <= ld");
     if (P == 0) return HB_OK;
+    if ((what == W_PRICE || what == W_JAC) && pl->S.n_opt == 0) return HB_OK;  // nothing to write
     if (!d_params || !d_out || (what == W_JAC && !d_out2)) return fail(HB_ERR_INVALID_ARGUMENT, "NULL device pointer");
     DeviceGuard guard(pl->device);
     if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");

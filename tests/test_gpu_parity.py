@@ -341,4 +341,10 @@ def test_full_size_objective_properties(torch_cuda, oracle):
     got = loss.cpu().numpy()[idx]
     assert np.array_equal(got == 1e10, want == 1e10)
     np.testing.assert_allclose(got, want, rtol=1e-8)
-    assert np.isfinite(loss.cpu().numpy()).all()
+    # non-finite losses (moment explosion of E[S^1.75] -> inf prices -> inf loss in the reference too,
+    # heston_calibrator.py:507-511 only screens NaN and <= 0) must be the oracle's non-finite losses
+    all_loss = loss.cpu().numpy()
+    odd = np.flatnonzero(~np.isfinite(all_loss))[:24]
+    if odd.size:
+        want_odd = oracle.objective_batch(MODE_FFT, params[odd], Kf, Tf, True, mk, S0, R, Q)
+        assert np.array_equal(all_loss[odd], want_odd, equal_nan=True), (params[odd], all_loss[odd], want_odd)

@@ -309,10 +309,10 @@ def test_normal_equations_match_oracle(torch_cuda, oracle, g_cal, mode, omode):
     scale_r = np.sqrt(want[:, 1:2])
     jj = np.sqrt(np.abs(want[:, [7, 12, 16, 19, 21]]))  # sqrt(diag(J^T J)) = column norms
     iu = np.triu_indices(5)
-    np.testing.assert_allclose(got[:, 2:7], want[:, 2:7], rtol=1e-4, atol=0)
+    # (J^T r)_c cancels when r is noise: bound it by the Cauchy-Schwarz scale ||J_c|| ||r||
+    assert (np.abs(got[:, 2:7] - want[:, 2:7]) <= 1e-5 * jj * scale_r + 1e-12).all()
     ref_scale = jj[:, iu[0]] * jj[:, iu[1]]
-    assert (np.abs(got[:, 7:] - want[:, 7:]) <= 1e-4 * ref_scale + 1e-12).all()
-    assert scale_r.min() >= 0
+    assert (np.abs(got[:, 7:] - want[:, 7:]) <= 1e-5 * ref_scale + 1e-12).all()
 
 
 # ---- full-size properties (BASELINE.json config 3: 65,536 sets x 32 maturities, N = 4096) -------------------------

@@ -257,7 +257,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t.item())
     e2e = slices_step * args.steps / te
-    assert np.isfinite(res[:, 0]).all()
+    # inf losses are legitimate (moment explosion of E[S^1.75]: the reference returns inf there too)
+    assert res.shape == (P, 22) and not np.isnan(res[:, 0]).any()
 
     if rank == 0:
         achieved = (P * N_MAT * 6 * FLOPS_PER_SLICE) / (ms / args.steps * 1e-3) / 1e12  # per GPU, TFLOP/s

@@ -27,13 +27,7 @@
 // formulas can be checked on the CPU by tests/test_host_math.py -- that is a
 // test harness, never a product path.
 #pragma once
-#include <math.h>
-
-#if defined(__CUDACC__)
-#define HB_HD __host__ __device__ __forceinline__
-#else
-#define HB_HD inline
-#endif
+#include "fp64_math.cuh"
 
 namespace hb {
 
@@ -42,23 +36,6 @@ struct cplx {
 };
 
 HB_HD cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
-
-HB_HD double rsqrt_f64(double x) {
-#if defined(__CUDA_ARCH__)
-    return rsqrt(x);
-#else
-    return 1.0 / sqrt(x);
-#endif
-}
-
-HB_HD void sincos_f64(double x, double* s, double* c) {
-#if defined(__CUDA_ARCH__)
-    sincos(x, s, c);
-#else
-    *s = sin(x);
-    *c = cos(x);
-#endif
-}
 
 // Parameter-set constants shared by every grid point of a (kappa,sigma,rho) class.
 struct ClassConst {
@@ -85,10 +62,11 @@ HB_HD StageA stage_a(const ClassConst& c, double ur, double ui) {
     const double zr = xr * xr - xi * xi + swr;
     const double zi = 2.0 * xr * xi + swi;
     // d = csqrt(z), principal branch (glibc csqrt: Re >= 0, Im carries sign of zi)
-    const double m = sqrt(zr * zr + zi * zi);  // |z| = |d|^2
+    double m, rm_;
+    sqrt_rsqrt(zr * zr + zi * zi, &m, &rm_);  // m = |z| = |d|^2
     const double h = 0.5 * (m + fabs(zr));
-    const double rh = rsqrt_f64(h);
-    const double big = h * rh;           // sqrt(h)
+    double big, rh;
+    sqrt_rsqrt(h, &big, &rh);            // sqrt(h), 1/sqrt(h)
     const double small = 0.5 * zi * rh;  // zi / (2 sqrt(h)), signed
     if (zr >= 0.0) {
         a.d.re = big;
@@ -101,21 +79,21 @@ HB_HD StageA stage_a(const ClassConst& c, double ur, double ui) {
     cplx num, den;
     if (xr >= 0.0) {
         den = {xr + a.d.re, xi + a.d.im};
-        const double r = 1.0 / (den.re * den.re + den.im * den.im);
+        const double r = rcp_nr(den.re * den.re + den.im * den.im);
         const cplx inv = {den.re * r, -den.im * r};
         num = cmul({-swr, -swi}, inv);
         a.g = cmul(num, inv);
     } else {
         num = {xr - a.d.re, xi - a.d.im};
-        const double r = 1.0 / (num.re * num.re + num.im * num.im);
+        const double r = rcp_nr(num.re * num.re + num.im * num.im);
         const cplx inv = {num.re * r, -num.im * r};
         den = cmul({-swr, -swi}, inv);
-        const double r2 = 1.0 / (den.re * den.re + den.im * den.im);
+        const double r2 = rcp_nr(den.re * den.re + den.im * den.im);
         a.g = cmul(num, {den.re * r2, -den.im * r2});
     }
     a.num = num;
     // q1 = num / (2 d) = num * conj(d) / (2 m)
-    const double rm = 0.5 / m;
+    const double rm = 0.5 * rm_;  // 1/(2 m): sqrt_rsqrt(m^2) returned 1/m
     a.q1 = cmul(num, {a.d.re * rm, -a.d.im * rm});
     return a;
 }
@@ -129,22 +107,22 @@ struct StageB {
 HB_HD StageB stage_b(const StageA& a, double T) {
     StageB b;
     // e = exp(-d T)                                          heston.cpp:59
-    const double ea = exp(-a.d.re * T);
+    const double ea = exp_nb(-a.d.re * T);
     double sn, cs;
-    sincos_f64(-a.d.im * T, &sn, &cs);
+    sincos_nb(-a.d.im * T, &sn, &cs);
     const cplx e = {ea * cs, ea * sn};
     const cplx ome = {1.0 - e.re, -e.im};  // 1 - e
     // ratio = (1-g e)/(1-g) = 1 + delta, delta = g (1-e)/(1-g)
     const cplx dl = cmul(a.q1, ome);
     const double x = 2.0 * dl.re + (dl.re * dl.re + dl.im * dl.im);  // |ratio|^2 - 1
-    const double lg = log1p(x);                                      // 2 Re log(ratio)
-    const double ar = atan2(dl.im, 1.0 + dl.re);                     // principal arg, as clog
+    const double lg = log1p_nb(x);                                     // 2 Re log(ratio)
+    const double ar = atan2_nb(dl.im, 1.0 + dl.re);                     // principal arg, as clog
     b.B.re = a.num.re * T - lg;
     b.B.im = a.num.im * T - 2.0 * ar;
     // Dq = num (1-e)/(1-g e)
     const cplx ge = cmul(a.g, e);
     const cplx n = {1.0 - ge.re, -ge.im};
-    const double rn = 1.0 / (n.re * n.re + n.im * n.im);
+    const double rn = rcp_nr(n.re * n.re + n.im * n.im);
     const cplx Q = cmul(ome, {n.re * rn, -n.im * rn});
     b.Dq = cmul(a.num, Q);
     return b;
@@ -161,9 +139,9 @@ struct SliceConst {
 HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui) {
     const double er = s.kts * b.B.re + s.v0s * b.Dq.re - ui * s.lsm;
     const double ei = s.kts * b.B.im + s.v0s * b.Dq.im + ur * s.lsm;
-    const double mag = exp(er);
+    const double mag = exp_nb(er);
     double sn, cs;
-    sincos_f64(ei, &sn, &cs);
+    sincos_nb(ei, &sn, &cs);
     return {mag * cs, mag * sn};
 }
 
@@ -172,9 +150,9 @@ HB_HD cplx heston_cf(double kappa, double theta, double sigma, double rho, doubl
                      double T, double S0, double r, double q) {
     const double L = log(S0);
     if (T <= 0.0) {  // heston.cpp:77-79: exp(i u ln S0)
-        const double mag = exp(-ui * L);
+        const double mag = exp_nb(-ui * L);
         double sn, cs;
-        sincos_f64(ur * L, &sn, &cs);
+        sincos_nb(ur * L, &sn, &cs);
         return {mag * cs, mag * sn};
     }
     ClassConst c = {kappa, sigma * sigma, rho * sigma};
@@ -188,7 +166,7 @@ HB_HD cplx heston_cf(double kappa, double theta, double sigma, double rho, doubl
 HB_HD cplx cm_inv_denominator(double v, double alpha) {
     const double a = alpha * alpha + alpha - v * v;
     const double b = (2.0 * alpha + 1.0) * v;
-    const double r = 1.0 / (a * a + b * b);
+    const double r = rcp_nr(a * a + b * b);
     return {a * r, -b * r};
 }
 

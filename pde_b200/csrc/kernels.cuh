@@ -487,8 +487,8 @@ refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restri
                 const double k = S.opt_lnk[o];
                 // e^{-i v_j k}, j = lane + 32 a: base rotation times a 32-step recurrence
                 double sb, cb, ss, cs;
-                sincos(-((double)lane * du) * k, &sb, &cb);
-                sincos(-(32.0 * du) * k, &ss, &cs);
+                sincos_nb(-((double)lane * du) * k, &sb, &cb);
+                sincos_nb(-(32.0 * du) * k, &ss, &cs);
                 cplx twd = {cb, sb};
                 const cplx st = {cs, ss};
                 double sum = 0.0;

@@ -16,3 +16,12 @@ extern "C" void hm_cf(const double* p, double ur, double ui, double T, double S0
     out[0] = z.re;
     out[1] = z.im;
 }
+
+// elementary routines of fp64_math.cuh (MUFU seeds emulated in float precision on the host)
+extern "C" void hm_exp(int n, const double* x, double* y) { for (int i = 0; i < n; ++i) y[i] = hb::exp_nb(x[i]); }
+extern "C" void hm_sincos(int n, const double* x, double* s, double* c) { for (int i = 0; i < n; ++i) hb::sincos_nb(x[i], s + i, c + i); }
+extern "C" void hm_log1p(int n, const double* x, double* y) { for (int i = 0; i < n; ++i) y[i] = hb::log1p_nb(x[i]); }
+extern "C" void hm_atan2(int n, const double* y, const double* x, double* a) { for (int i = 0; i < n; ++i) a[i] = hb::atan2_nb(y[i], x[i]); }
+extern "C" void hm_div(int n, const double* a, const double* b, double* q) { for (int i = 0; i < n; ++i) q[i] = hb::div_nr(a[i], b[i]); }
+extern "C" void hm_rcp(int n, const double* a, double* q) { for (int i = 0; i < n; ++i) q[i] = hb::rcp_nr(a[i]); }
+extern "C" void hm_sqrt(int n, const double* a, double* s, double* r) { for (int i = 0; i < n; ++i) hb::sqrt_rsqrt(a[i], s + i, r + i); }

@@ -1,0 +1,163 @@
+"""CPU checks of the product's device math (pde_b200/csrc/fp64_math.cuh, heston_math.cuh).
+
+The headers are compiled as plain C++ by tests/host_math_check.cpp (MUFU seeds emulated in
+float precision) so the FORMULAS -- minimax tables, Newton steps, argument reductions, the
+cancellation-free little-trap restatement -- are verified without a GPU.  This harness is test
+infrastructure only; nothing under pde_b200/ builds or loads it, and the GPU tests
+(tests/test_gpu_parity.py) check the same code compiled by nvcc.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+S0, R, Q = 100.0, 0.05, 0.02
+LB = np.array([0.1, 0.01, 0.01, -0.99, 0.01])
+UB = np.array([10.0, 1.0, 2.0, 0.99, 1.0])
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+@pytest.fixture(scope="module")
+def hm(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("hm") / "libhm.so")
+    flags = ["-mfma"] if "fma" in open("/proc/cpuinfo").read() else []
+    subprocess.run(["g++", "-O2", *flags, "-fPIC", "-shared", os.path.join(ROOT, "tests", "host_math_check.cpp"),
+                    "-o", out], check=True)
+    return C.CDLL(out)
+
+
+def _ulps(got, exact):
+    """|got - exact| in units of 2^-52 |exact| (exact: list of mpmath numbers)."""
+    import mpmath as mp
+
+    worst = 0.0
+    for g, e in zip(got, exact):
+        if e == 0:
+            assert g == 0.0
+            continue
+        worst = max(worst, float(abs(mp.mpf(float(g)) - e) / abs(e) * 2 ** 52))
+    return worst
+
+
+def test_elementary_functions_within_2ulp(hm):
+    import mpmath as mp
+
+    mp.mp.dps = 40
+    rng = np.random.default_rng(0)
+    n = 3000
+    f = lambda t: mp.mpf(float(t))
+    # exp: normal results; subnormal/underflow/overflow checked separately
+    x = np.concatenate([rng.uniform(-700, 709, n), rng.uniform(-1, 1, n), [0.0, 1e-300, -1e-300]])
+    y = np.empty_like(x)
+    hm.hm_exp(x.size, _p(x), _p(y))
+    assert _ulps(y, [mp.exp(f(t)) for t in x]) < 1.5
+    x = np.array([-1e4, -1500.0, -746.0, -740.0, 710.0, 1500.0, np.inf, -np.inf])
+    y = np.empty_like(x)
+    hm.hm_exp(x.size, _p(x), _p(y))
+    assert y[0] == 0 and y[1] == 0 and y[2] == 0 and y[7] == 0
+    assert abs(y[3] - np.exp(-740.0)) <= 2 * 4.94e-324 and np.isinf(y[4]) and np.isinf(y[5]) and np.isinf(y[6])
+    # sincos: the phases of this path (|x| up to ~1e6), quadrant boundaries included
+    x = np.concatenate([rng.uniform(-6000, 6000, n), rng.uniform(-1.5e6, 1.5e6, n), rng.uniform(-1, 1, n),
+                        np.arange(-200, 200) * (np.pi / 2), [0.0, 1e-300]])
+    s, c = np.empty_like(x), np.empty_like(x)
+    hm.hm_sincos(x.size, _p(x), _p(s), _p(c))
+    exact_s, exact_c = [mp.sin(f(t)) for t in x], [mp.cos(f(t)) for t in x]
+    big = np.abs(np.array([float(e) for e in exact_s])) > 1e-3  # relative error only away from zeros
+    assert _ulps(s[big], [e for e, b in zip(exact_s, big) if b]) < 2.0
+    bigc = np.abs(np.array([float(e) for e in exact_c])) > 1e-3
+    assert _ulps(c[bigc], [e for e, b in zip(exact_c, bigc) if b]) < 2.0
+    # near the zeros of sin/cos: absolute error against the exact value
+    assert max(abs(float(mp.mpf(float(g)) - e)) for g, e in zip(s, exact_s)) < 3e-16
+    assert max(abs(float(mp.mpf(float(g)) - e)) for g, e in zip(c, exact_c)) < 3e-16
+    # far outside the reducible range: finite, bounded output (the caller's magnitude is 0 there)
+    x = np.array([1e9, -3e12, 1e20, np.inf])
+    s, c = np.empty_like(x), np.empty_like(x)
+    hm.hm_sincos(x.size, _p(x), _p(s), _p(c))
+    assert np.isfinite(s).all() and np.isfinite(c).all() and np.abs(s).max() < 2 and np.abs(c).max() < 2
+    # log1p
+    x = np.concatenate([rng.uniform(-0.999, 10, n), 10 ** rng.uniform(-20, 0, n) * rng.choice([-1, 1], n),
+                        10 ** rng.uniform(0, 30, n), [-1 + 1e-15, 1e-300, 0.0]])
+    y = np.empty_like(x)
+    hm.hm_log1p(x.size, _p(x), _p(y))
+    assert _ulps(y, [mp.log1p(f(t)) for t in x]) < 1.5
+    x = np.array([-1.0, -2.0, np.inf])
+    y = np.empty_like(x)
+    hm.hm_log1p(x.size, _p(x), _p(y))
+    assert y[0] == -np.inf and np.isnan(y[1]) and y[2] == np.inf
+    # atan2: all quadrants, tiny and huge ratios, the 1 + delta shape used by stage B
+    yy = np.concatenate([rng.normal(size=n), 10 ** rng.uniform(-12, 0, n) * rng.choice([-1, 1], n),
+                         rng.normal(size=200) * 1e8, [0.0, 1.0, -1.0, 0.0]])
+    xx = np.concatenate([rng.normal(size=n), 1 + rng.normal(size=n) * 1e-3, rng.normal(size=200), [1.0, 0.0, 0.0, -1.0]])
+    a = np.empty_like(xx)
+    hm.hm_atan2(xx.size, _p(yy), _p(xx), _p(a))
+    assert _ulps(a, [mp.atan2(f(p), f(q)) for p, q in zip(yy, xx)]) < 2.0
+    # division / reciprocal / sqrt: compare with IEEE operations
+    aa = rng.normal(size=n) * 10 ** rng.uniform(-30, 30, n)
+    bb = rng.normal(size=n) * 10 ** rng.uniform(-30, 30, n)
+    q = np.empty_like(aa)
+    hm.hm_div(n, _p(aa), _p(bb), _p(q))
+    assert np.max(np.abs(q - aa / bb) / np.abs(aa / bb)) <= 2 ** -52
+    hm.hm_rcp(n, _p(bb), _p(q))
+    assert np.max(np.abs(q * bb - 1)) <= 2 ** -51
+    pos = np.abs(aa)
+    sq, rs = np.empty_like(pos), np.empty_like(pos)
+    hm.hm_sqrt(n, _p(pos), _p(sq), _p(rs))
+    assert np.max(np.abs(sq - np.sqrt(pos)) / np.sqrt(pos)) <= 2 ** -52
+    assert np.max(np.abs(rs * np.sqrt(pos) - 1)) <= 2 ** -50
+
+
+def _hm_cf(hm, p, v, ui, T):
+    p = np.ascontiguousarray(p, dtype=float)
+    v = np.ascontiguousarray(v, dtype=float)
+    out = np.empty((v.size, 2))
+    hm.hm_cf_grid(_p(p), C.c_int(v.size), _p(v), C.c_double(ui), C.c_double(T), C.c_double(S0), C.c_double(R),
+                  C.c_double(Q), _p(out))
+    return out[:, 0] + 1j * out[:, 1]
+
+
+def test_cf_formulas_match_reference_golden(hm, g_cf):
+    """The real-arithmetic, cancellation-free restatement against the reference's CF values."""
+    params, Ts = g_cf["params"], g_cf["T"]
+    worst_well, worst_ill = 0.0, 0.0
+    for i, p in enumerate(params):
+        for m, T in enumerate(Ts):
+            for v, want in ((g_cf["v_fft"], g_cf["cf_fft"][i, m]), (g_cf["v_rg"], g_cf["cf_rg"][i, m])):
+                got = _hm_cf(hm, p, v, float(g_cf["ui"]), T)
+                rel = np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-290))
+                if p[2] >= 0.02:
+                    worst_well = max(worst_well, rel)
+                else:
+                    worst_ill = max(worst_ill, rel)
+    assert worst_well < 1e-10, worst_well
+    assert worst_ill < 2e-9, worst_ill  # sigma = 0.01 corners: the reference's own noise (test_conditioning.py)
+
+
+def test_cf_formulas_are_closer_to_exact_than_the_reference(hm, oracle, g_cf):
+    """Against the 80-bit yardstick the product formulas carry ~1e-13, including the small-sigma
+    corners where the reference's subtraction xi - d and log(ratio) lose up to 6 digits."""
+    v = 0.25 * np.arange(0, 4096, 3)
+    worst_ours, worst_ref = 0.0, 0.0
+    for p in g_cf["params"]:
+        for T in (0.1, 1.0):
+            exact = oracle.cf_ld_grid(p, T, v, -1.75, S0, R, Q)
+            ours = _hm_cf(hm, p, v, -1.75, T)
+            ref = oracle.cf_grid(p, [T], v, -1.75, S0, R, Q)[0, 0]
+            ok = np.abs(exact) > 1e-280
+            worst_ours = max(worst_ours, np.max(np.abs(ours - exact)[ok] / np.abs(exact)[ok]))
+            worst_ref = max(worst_ref, np.max(np.abs(ref - exact)[ok] / np.abs(exact)[ok]))
+    assert worst_ours < 5e-12, worst_ours
+    assert worst_ref > 10 * worst_ours  # documents why parity is asserted at 4x tolerance for sigma < 0.02
+
+
+def test_cf_general_u(hm, g_cf):
+    for i, p in enumerate(g_cf["params"][:8]):
+        for u, want in zip(g_cf["u_gen"], g_cf["cf_gen"][i]):
+            got = _hm_cf(hm, p, [u.real], u.imag, 0.7)[0]
+            assert abs(got - want) / abs(want) < 1e-10

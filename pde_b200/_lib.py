@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libheston_b200.so")
+# PDE_B200_LIB points at an alternative build of the same library (kernel-shape experiments)
+LIB_PATH = os.environ.get("PDE_B200_LIB") or os.path.join(HERE, "csrc", "libheston_b200.so")
 
 HB_OK, HB_ERR_INVALID_ARGUMENT, HB_ERR_INVALID_PARAMETER, HB_ERR_CUDA, HB_ERR_STATE = range(5)
 HB_MODE_REFGRID, HB_MODE_FFT = 0, 1

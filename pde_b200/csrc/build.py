@@ -11,7 +11,7 @@ HEADERS = ["kernels.cuh", "fft_smem.cuh", "heston_math.cuh", os.path.join("..", 
 TARGET = os.path.join(HERE, "libheston_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "1886",
+    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "1886,177",
 ]
 
 

@@ -98,46 +98,51 @@ __device__ __forceinline__ void fill_twiddles(double2* tw, int tid, int nthreads
 
 // One full radix-8 pass, in place, over slices base + g*N for g < gmax; only slices
 // g < count hold data (count is block-uniform), but every thread executes all gmax
-// barriers.  LINEAR_IN: the pass reads an unswizzled slice (as landed by a bulk copy)
-// and writes the swizzled layout.
+// barriers.  A thread owns PER = ceil((N/8)/NT) butterflies and keeps all of them in
+// registers across the barrier (the pass is in place).  LINEAR_IN: the pass reads an
+// unswizzled slice (as landed by a bulk copy) and writes the swizzled layout.
 template <int N, int NT, bool LINEAR_IN = false>
 __device__ __forceinline__ void fft_pass(double2* base, int count, int gmax, const double2* tw, int Ns, int tid) {
     constexpr int NB = N / 8;
-    static_assert(NB <= NT, "in-place pass: one butterfly per thread");
-    const int b = tid;
-    const bool on = b < NB;
-    const int bm = b & (Ns - 1);
-    cplx p[8];
-    if (on && Ns > 1) {
-        double2 w = tw[bm * (NB / Ns)];
-        twiddle_powers({w.x, w.y}, p);
-    }
-    const int j0 = (b - bm) * 8 + bm;
+    constexpr int PER = (NB + NT - 1) / NT;
+    static_assert(NB % NT == 0 || NB < NT, "butterflies must tile over the block");
 #pragma unroll 1
     for (int g = 0; g < gmax; ++g) {
         double2* s = base + (size_t)g * N;
-        const bool act = on && g < count;
-        cplx v[8];
-        if (act) {
+        cplx v[PER][8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (LINEAR_IN) {
-                    double2 t = s[b + r * NB];
-                    v[r] = {t.x, t.y};
-                } else {
-                    v[r] = lds_c(s, b + r * NB);
+        for (int u = 0; u < PER; ++u) {
+            const int b = tid + u * NT;
+            if (b < NB && g < count) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if (LINEAR_IN) {
+                        double2 t = s[b + r * NB];
+                        v[u][r] = {t.x, t.y};
+                    } else {
+                        v[u][r] = lds_c(s, b + r * NB);
+                    }
                 }
             }
         }
         __syncthreads();  // loads of slice g done; stores of slice g-1 visible
-        if (act) {
-            if (Ns > 1) {
 #pragma unroll
-                for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], p[r]);
+        for (int u = 0; u < PER; ++u) {
+            const int b = tid + u * NT;
+            if (b < NB && g < count) {
+                const int bm = b & (Ns - 1);
+                if (Ns > 1) {
+                    double2 w = tw[bm * (NB / Ns)];
+                    cplx p[8];
+                    twiddle_powers({w.x, w.y}, p);
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) v[u][r] = cmul(v[u][r], p[r]);
+                }
+                dft8(v[u]);
+                const int j0 = (b - bm) * 8 + bm;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) sts_c(s, j0 + r * Ns, v[u][bitrev3(r)]);
             }
-            dft8(v);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) sts_c(s, j0 + r * Ns, v[bitrev3(r)]);
         }
     }
     if (gmax == 1) __syncthreads();  // a lone slice has no neighbour barrier to fence its stores

@@ -290,7 +290,19 @@ __device__ __forceinline__ double finish_price(double call, bool is_call, double
 // Fused Carr-Madan FFT job kernel
 // ============================================================================================
 
-template <int N, int NT>
+// Launch shapes of the fused kernel (threads per CTA, grid points interleaved per thread).
+#ifndef HB_NT4096
+#define HB_NT4096 512
+#endif
+// Measured on B200 (slices/s at 4736 sets, profiles/r01_shape_sweep.txt): 512x1 11.78 M,
+// 640x1 11.43 M, 512x2 11.22 M, 768x1 10.68 M, 256x2 10.62 M, 256x4 9.88 M, 1024x1 9.80 M --
+// 128 registers/thread is the knee: more warps spill, explicit interleave does not fit.
+#ifndef HB_IL4096
+#define HB_IL4096 1
+#endif
+constexpr int kNT4096 = HB_NT4096, kIL4096 = HB_IL4096, kNT512 = 128, kIL512 = 1;
+
+template <int N, int NT, int IL>
 __global__ void __launch_bounds__(NT, 1)
 fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
                double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int gmax,
@@ -343,28 +355,43 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             const int count = grp.count;
             // ---- K1: characteristic function on the damped grid -> x_j in shared memory ----
             {
+                // IL grid points per thread are evaluated side by side: the routines are straight-line
+                // code, so ptxas interleaves the IL independent dependency chains (the kernel is
+                // latency-bound at 4 warps/scheduler otherwise: stall_wait 38 %, profiles/r01_b).
                 const ClassConst cc = grp.cc;
+                static_assert(IL == 1 || N % (NT * IL) == 0, "grid points must tile over threads x interleave");
 #pragma unroll 1
-                for (int j = tid; j < N; j += NT) {
-                    const double v = gc.eta * (double)j;
-                    const StageA a = stage_a(cc, v, gc.ui);
-                    cplx tab = cm_inv_denominator(v, gc.alpha);
-                    // Simpson weight times e^{i b v_j} = (-1)^j   
-                    const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
-                    tab.re *= wgt;
-                    tab.im *= wgt;
-                    StageB b = {};
+                for (int j0 = tid; j0 < N; j0 += NT * IL) {
+                    double v[IL];
+                    StageA a[IL];
+                    cplx tab[IL];
+#pragma unroll
+                    for (int q = 0; q < IL; ++q) {
+                        const int j = j0 + q * NT;
+                        v[q] = gc.eta * (double)j;
+                        a[q] = stage_a(cc, v[q], gc.ui);
+                        tab[q] = cm_inv_denominator(v[q], gc.alpha);
+                        // Simpson weight times e^{i b v_j} = (-1)^j   
+                        const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
+                        tab[q].re *= wgt;
+                        tab[q].im *= wgt;
+                    }
+                    StageB b[IL] = {};
                     double Tprev = -1.0;
 #pragma unroll 1
                     for (int g = 0; g < count; ++g) {
                         const SubSlice& s = grp.s[g];
                         if (s.T != Tprev) {
-                            b = stage_b(a, s.T);
+#pragma unroll
+                            for (int q = 0; q < IL; ++q) b[q] = stage_b(a[q], s.T);
                             Tprev = s.T;
                         }
                         const SliceConst sc = {s.kts, s.v0s, s.lsm};
-                        const cplx phi = stage_f(b, sc, v, gc.ui);
-                        sts_c(slices + (size_t)g * N, j, cmul(phi, tab));
+#pragma unroll
+                        for (int q = 0; q < IL; ++q) {
+                            const cplx phi = stage_f(b[q], sc, v[q], gc.ui);
+                            sts_c(slices + (size_t)g * N, j0 + q * NT, cmul(phi, tab[q]));
+                        }
                     }
                 }
             }

@@ -129,7 +129,7 @@ def cpu_reference_rate(seconds_budget, n_sets_hint=None):
 
     ref = Reference()
     K, T = surface()
-    cores = ref.num_threads()
+    cores = ref.use_all_cores()
     rows = fd_variants(sobol_sets(4096)[:512])
     ref.price_surface_batch(rows[:1], K, T, S0, R, Q)  # warm
     done, t0 = 0, time.perf_counter()
@@ -291,6 +291,7 @@ def run_ours(args):
                 from oracle.oracle import MODE_FFT, Oracle
 
                 orc = Oracle()
+                orc.use_all_cores()
                 rows = fd_variants(sobol_sets(64))
                 t0 = time.perf_counter()
                 n_done = 0

@@ -415,6 +415,14 @@ void orc_cf_grid(int P, const double *params, int M, const double *T, int n_u, c
     }
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -60,6 +60,11 @@ class Oracle:
     def num_threads(self) -> int:
         return int(self.lib.orc_num_threads())
 
+    def use_all_cores(self) -> int:
+        """OpenMP threads = cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+        self.lib.orc_set_num_threads(len(os.sched_getaffinity(0)))
+        return self.num_threads()
+
     def cf(self, p, u, T, S0, r, q) -> complex:
         p_, pp = _d(p)
         out = np.empty(2)
@@ -196,6 +201,11 @@ class Reference:
 
     def num_threads(self) -> int:
         return int(self.lib.ref_num_threads())
+
+    def use_all_cores(self) -> int:
+        """OpenMP threads = cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+        self.lib.ref_set_num_threads(len(os.sched_getaffinity(0)))
+        return self.num_threads()
 
     def _chk(self, rc):
         if rc:

@@ -153,6 +153,15 @@ int ref_greeks(const double* p, double K, double T, double S0, double r, double 
     }
 }
 
+// torchrun exports OMP_NUM_THREADS=1; the CPU baseline must say how many threads it really used.
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ref_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

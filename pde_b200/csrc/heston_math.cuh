@@ -98,6 +98,69 @@ HB_HD StageA stage_a(const ClassConst& c, double ur, double ui) {
     return a;
 }
 
+// Stage A for a point of the damped grid together with the Carr-Madan weight
+//   tab = wgt / (alpha^2 + alpha - v^2 + i (2 alpha + 1) v)                         heston.cpp:117
+// whose reciprocal's Newton steps are interleaved with the first square root's (two chains).
+HB_HD StageA stage_a_tab(const ClassConst& c, double v, double ui, double alpha, double wgt, cplx* tab) {
+    StageA a;
+    const double xr = c.kappa + c.rs * ui;
+    const double xi = -c.rs * v;
+    const double wr = v * v - ui * ui - ui;
+    const double wi = 2.0 * v * ui + v;
+    const double ta = alpha * alpha + alpha - v * v;
+    const double tb = (2.0 * alpha + 1.0) * v;
+    const double swr = c.sigma2 * wr, swi = c.sigma2 * wi;
+    const double zr = xr * xr - xi * xi + swr;
+    const double zi = 2.0 * xr * xi + swi;
+    const double m2 = fma_(zr, zr, zi * zi);
+    const double tn = fma_(ta, ta, tb * tb);
+    // m = sqrt(m2) = |z| and 1/m (coupled Newton)   ||   1/tn
+    const double y = rsqrt_seed(m2);
+    double yt = rcp_seed(tn);
+    double g = m2 * y, h = 0.5 * y;
+    double et = fma_(-tn, yt, 1.0);
+    double r = fma_(-g, h, 0.5);
+    yt = fma_(yt, et, yt);
+    g = fma_(g, r, g);
+    h = fma_(h, r, h);
+    et = fma_(-tn, yt, 1.0);
+    r = fma_(-g, h, 0.5);
+    yt = fma_(yt, et, yt);
+    g = fma_(g, r, g);
+    h = fma_(h, r, h);
+    const double dd = fma_(-g, g, m2);
+    const double m = fma_(dd, h, g);
+    const double rm = h;  // 1/(2 m)
+    yt *= wgt;
+    tab->re = ta * yt;
+    tab->im = -tb * yt;
+    // d = csqrt(z), principal branch
+    const double hh = 0.5 * (m + fabs(zr));
+    double big, rh;
+    sqrt_rsqrt(hh, &big, &rh);
+    const double small = 0.5 * zi * rh;
+    a.d.re = (zr >= 0.0) ? big : fabs(small);
+    a.d.im = (zr >= 0.0) ? small : copysign(big, zi);
+    cplx num, den;
+    if (xr >= 0.0) {
+        den = {xr + a.d.re, xi + a.d.im};
+        const double rr = rcp_nr(den.re * den.re + den.im * den.im);
+        const cplx inv = {den.re * rr, -den.im * rr};
+        num = cmul({-swr, -swi}, inv);
+        a.g = cmul(num, inv);
+    } else {
+        num = {xr - a.d.re, xi - a.d.im};
+        const double rr = rcp_nr(num.re * num.re + num.im * num.im);
+        const cplx inv = {num.re * rr, -num.im * rr};
+        den = cmul({-swr, -swi}, inv);
+        const double r2 = rcp_nr(den.re * den.re + den.im * den.im);
+        a.g = cmul(num, {den.re * r2, -den.im * r2});
+    }
+    a.num = num;
+    a.q1 = cmul(num, {a.d.re * rm, -a.d.im * rm});
+    return a;
+}
+
 // theta/v0-independent stage, one per (stage A, T).
 struct StageB {
     cplx B;   // (xi-d) T - 2 log((1 - g e)/(1 - g))
@@ -107,22 +170,19 @@ struct StageB {
 HB_HD StageB stage_b(const StageA& a, double T) {
     StageB b;
     // e = exp(-d T)                                          heston.cpp:59
-    const double ea = exp_nb(-a.d.re * T);
-    double sn, cs;
-    sincos_nb(-a.d.im * T, &sn, &cs);
-    const cplx e = {ea * cs, ea * sn};
+    cplx e;
+    cexp_nb(-a.d.re * T, -a.d.im * T, &e.re, &e.im);
     const cplx ome = {1.0 - e.re, -e.im};  // 1 - e
     // ratio = (1-g e)/(1-g) = 1 + delta, delta = g (1-e)/(1-g)
     const cplx dl = cmul(a.q1, ome);
-    const double x = 2.0 * dl.re + (dl.re * dl.re + dl.im * dl.im);  // |ratio|^2 - 1
-    const double lg = log1p_nb(x);                                     // 2 Re log(ratio)
-    const double ar = atan2_nb(dl.im, 1.0 + dl.re);                     // principal arg, as clog
+    const cplx ge = cmul(a.g, e);
+    const cplx n = {1.0 - ge.re, -ge.im};  // 1 - g e
+    // lg = 2 Re log(ratio), ar = principal arg (as clog), rn = 1/|1 - g e|^2 -- evaluated together
+    double lg, ar, rn;
+    clog1p_rcp_nb(dl.re, dl.im, n.re * n.re + n.im * n.im, &lg, &ar, &rn);
     b.B.re = a.num.re * T - lg;
     b.B.im = a.num.im * T - 2.0 * ar;
     // Dq = num (1-e)/(1-g e)
-    const cplx ge = cmul(a.g, e);
-    const cplx n = {1.0 - ge.re, -ge.im};
-    const double rn = rcp_nr(n.re * n.re + n.im * n.im);
     const cplx Q = cmul(ome, {n.re * rn, -n.im * rn});
     b.Dq = cmul(a.num, Q);
     return b;
@@ -139,10 +199,9 @@ struct SliceConst {
 HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui) {
     const double er = s.kts * b.B.re + s.v0s * b.Dq.re - ui * s.lsm;
     const double ei = s.kts * b.B.im + s.v0s * b.Dq.im + ur * s.lsm;
-    const double mag = exp_nb(er);
-    double sn, cs;
-    sincos_nb(ei, &sn, &cs);
-    return {mag * cs, mag * sn};
+    cplx phi;
+    cexp_nb(er, ei, &phi.re, &phi.im);
+    return phi;
 }
 
 // Full CF for arbitrary complex u (the bound API characteristic_function(u,T,S0,r,q)).

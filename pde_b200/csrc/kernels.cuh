@@ -369,12 +369,9 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     for (int q = 0; q < IL; ++q) {
                         const int j = j0 + q * NT;
                         v[q] = gc.eta * (double)j;
-                        a[q] = stage_a(cc, v[q], gc.ui);
-                        tab[q] = cm_inv_denominator(v[q], gc.alpha);
                         // Simpson weight times e^{i b v_j} = (-1)^j   
                         const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
-                        tab[q].re *= wgt;
-                        tab[q].im *= wgt;
+                        a[q] = stage_a_tab(cc, v[q], gc.ui, gc.alpha, wgt, &tab[q]);
                     }
                     StageB b[IL] = {};
                     double Tprev = -1.0;

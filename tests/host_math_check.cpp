@@ -25,3 +25,11 @@ extern "C" void hm_atan2(int n, const double* y, const double* x, double* a) { f
 extern "C" void hm_div(int n, const double* a, const double* b, double* q) { for (int i = 0; i < n; ++i) q[i] = hb::div_nr(a[i], b[i]); }
 extern "C" void hm_rcp(int n, const double* a, double* q) { for (int i = 0; i < n; ++i) q[i] = hb::rcp_nr(a[i]); }
 extern "C" void hm_sqrt(int n, const double* a, double* s, double* r) { for (int i = 0; i < n; ++i) hb::sqrt_rsqrt(a[i], s + i, r + i); }
+
+// fused, hand-interleaved routines
+extern "C" void hm_cexp(int n, const double* x, const double* y, double* re, double* im) {
+    for (int i = 0; i < n; ++i) hb::cexp_nb(x[i], y[i], re + i, im + i);
+}
+extern "C" void hm_clog1p(int n, const double* dr, const double* di, const double* w, double* lg, double* ar, double* rw) {
+    for (int i = 0; i < n; ++i) hb::clog1p_rcp_nb(dr[i], di[i], w[i], lg + i, ar + i, rw + i);
+}

@@ -61,7 +61,8 @@ int hb_device_count(void);          /* 0 when no CUDA device is usable */
 
 /* ---- plan: grid constants, tables, workspace ------------------------------------------ */
 
-/* mode FFT: n_grid in {512, 4096}, eta > 0, alpha > 0 (reference docs: 4096, 0.25; alpha
+/* mode FFT: n_grid = 512 or a power of two in [4096, 65536] (grids above 4096 are transformed as
+ * R = n_grid/4096 decimated on-chip sub-transforms), eta > 0, alpha > 0 (reference docs: 4096, 0.25; alpha
  * 0.75 from heston.hpp:261).  mode REFGRID: n_grid/eta are ignored (1024 / 0.01 fixed by
  * heston.cpp:126-127), alpha must be 0.75.  `device` is a CUDA ordinal. */
 int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, hb_plan** out);

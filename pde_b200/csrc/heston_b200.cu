@@ -81,7 +81,9 @@ struct BlobBuilder {
 
 struct hb_plan {
     int mode = HB_MODE_FFT;
-    int N = 4096;
+    int N = 4096;     // full grid length
+    int Nsub = 4096;  // on-chip transform length (512 or 4096); N = R * Nsub
+    int R = 1;
     int device = 0;
     int sm_count = 0;
     double eta = 0.25, alpha = 0.75;
@@ -145,11 +147,11 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
     if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
     const SurfaceDev& S = pl->S;
     const int n = S.n_opt, M = S.n_mat, V = (what >= W_NEQ) ? 6 : 1;
-    GridConst gc = {pl->eta, pl->alpha, -(pl->alpha + 1.0), pl->eta / 3.0};
+    GridConst gc = {pl->eta, pl->alpha, -(pl->alpha + 1.0), pl->eta / 3.0, pl->R, pl->N};
     const size_t row_bytes = (size_t)6 * std::max(n, 1) * sizeof(double);
 
     if (pl->mode == HB_MODE_FFT) {
-        const int gmax = gmax_for(pl->N);
+        const int gmax = gmax_for(pl->Nsub);
         const int g0 = ((V > 1 ? 3 * M : M) + gmax - 1) / gmax, g1 = (M + gmax - 1) / gmax;
         const int groups = g0 + (V > 1 ? 3 : 0) * g1;
         const int max_ctas = pl->sm_count;
@@ -163,8 +165,8 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
             if (rc) return rc;
             scratch = (double*)pl->scratch.dev;
         }
-        const size_t smem = fft_smem_bytes(pl->N, gmax);
-        if (pl->N == 4096) {
+        const size_t smem = fft_smem_bytes(pl->Nsub, gmax);
+        if (pl->Nsub == 4096) {
             fft_job_kernel<4096, kNT4096, kIL4096><<<grid, kNT4096, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
                                                               scratch, gmax, split ? 1 : 0);
         } else {
@@ -262,8 +264,8 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     *out = nullptr;
     if (mode != HB_MODE_REFGRID && mode != HB_MODE_FFT) return fail(HB_ERR_INVALID_ARGUMENT, "unknown mode");
     if (mode == HB_MODE_FFT) {
-        if (n_grid != 4096 && n_grid != 512)
-            return fail(HB_ERR_STATE, "FFT grid size must be 512 or 4096 (one slice per CTA's shared memory)");
+        const bool ok = n_grid == 512 || (n_grid >= 4096 && n_grid <= 65536 && (n_grid & (n_grid - 1)) == 0);
+        if (!ok) return fail(HB_ERR_STATE, "FFT grid size must be 512 or a power of two in [4096, 65536]");
         if (!(eta > 0.0) || !(alpha > 0.0)) return fail(HB_ERR_INVALID_ARGUMENT, "eta and alpha must be positive");
     } else {
         if (alpha != 0.75) return fail(HB_ERR_INVALID_ARGUMENT, "refgrid mode is defined for alpha = 0.75 (heston.hpp:261)");
@@ -281,6 +283,8 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     hb_plan* pl = new hb_plan();
     pl->mode = mode;
     pl->N = n_grid;
+    pl->Nsub = (mode == HB_MODE_FFT && n_grid >= 4096) ? 4096 : n_grid;
+    pl->R = pl->N / pl->Nsub;
     pl->eta = eta;
     pl->alpha = alpha;
     pl->device = device;
@@ -290,7 +294,7 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     std::memcpy(pl->bd.lb, lb, sizeof lb);
     std::memcpy(pl->bd.ub, ub, sizeof ub);
     if (mode == HB_MODE_FFT) {
-        int rc = (n_grid == 4096) ? set_smem(fft_job_kernel<4096, kNT4096, kIL4096>, fft_smem_bytes(4096, gmax_for(4096)))
+        int rc = (n_grid >= 4096) ? set_smem(fft_job_kernel<4096, kNT4096, kIL4096>, fft_smem_bytes(4096, gmax_for(4096)))
                                   : set_smem(fft_job_kernel<512, kNT512, kIL512>, fft_smem_bytes(512, gmax_for(512)));
         if (rc) {
             delete pl;
@@ -369,7 +373,7 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     std::vector<int> mat_off(M + 1, 0), opt_orig, opt_bin, need_off(M + 1, 0), need_q;
     std::vector<double> opt_frac, opt_s0, opt_s1, opt_lnk, opt_kdisc;
     std::vector<uint8_t> opt_call;
-    const int NB = std::max(N / 8, 1);
+    const int Nsub = pl->Nsub, NB = std::max(Nsub / 8, 1);
     for (int m = 0; m < M; ++m) {
         const double T = mats[m];
         const double disc = std::exp(-rate * T);  // heston.cpp:106
@@ -397,8 +401,8 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                     opt_frac.push_back((k - km) / lambda);
                     opt_s0.push_back(std::exp(-alpha * km) / kPi);
                     opt_s1.push_back(std::exp(-alpha * km1) / kPi);
-                    qs.push_back(mm % NB);
-                    qs.push_back((mm + 1) % NB);
+                    qs.push_back((mm % Nsub) % NB);  // last-pass butterfly of the on-chip transform
+                    qs.push_back(((mm + 1) % Nsub) % NB);
                 }
             } else {
                 opt_bin.push_back(0);

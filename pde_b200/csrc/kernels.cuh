@@ -55,6 +55,12 @@ struct SurfaceDev {
 
 struct GridConst {
     double eta, alpha, ui, w0;  // ui = -(alpha+1), w0 = eta/3
+    // Grids longer than one CTA's shared memory (N = R * Nsub, e.g. 16384 = 4 * 4096; a 256 KiB
+    // slice does not fit 227 KB) are transformed by decimation in time: phase ph holds the points
+    // j = ph + R jj, its Nsub-point FFT Y_ph is taken on chip, and
+    //   X[m] = sum_ph W_N^{ph m} Y_ph[m mod Nsub]
+    // is accumulated only at the quoted bins.  R = 1 is the plain single-transform path.
+    int R, n_full;
 };
 
 struct Bounds {
@@ -353,11 +359,10 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             if (tid == 0) fill_group(grp, js, S, cls, V, t0, n_total, gmax);
             __syncthreads();
             const int count = grp.count;
+            for (int ph = 0; ph < gc.R; ++ph) {
             // ---- K1: characteristic function on the damped grid -> x_j in shared memory ----
             {
-                // IL grid points per thread are evaluated side by side: the routines are straight-line
-                // code, so ptxas interleaves the IL independent dependency chains (the kernel is
-                // latency-bound at 4 warps/scheduler otherwise: stall_wait 38 %, profiles/r01_b).
+                // IL grid points per thread are evaluated side by side (IL = 1 measured best, see above).
                 const ClassConst cc = grp.cc;
                 static_assert(IL == 1 || N % (NT * IL) == 0, "grid points must tile over threads x interleave");
 #pragma unroll 1
@@ -367,7 +372,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     cplx tab[IL];
 #pragma unroll
                     for (int q = 0; q < IL; ++q) {
-                        const int j = j0 + q * NT;
+                        const int j = ph + gc.R * (j0 + q * NT);  // index on the full N-point grid
                         v[q] = gc.eta * (double)j;
                         // Simpson weight times e^{i b v_j} = (-1)^j   
                         const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
@@ -402,24 +407,38 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 fft_last_pass_pruned<N, NT>(slices + (size_t)g * N, tw, S.need_q + q0, S.need_off[mat + 1] - q0, tid);
             }
             __syncthreads();
-            // ---- K3: log-strike interpolation, clamp, parity -> price rows ----
+            // ---- K3: log-strike interpolation (accumulated over phases), clamp, parity -> price rows ----
             for (int g = 0; g < count; ++g) {
                 const SubSlice& s = grp.s[g];
                 const double2* sl = slices + (size_t)g * N;
                 const int o1 = S.mat_off[s.mat + 1];
                 for (int o = S.mat_off[s.mat] + tid; o < o1; o += NT) {
                     const int bin = S.opt_bin[o];
+                    double* dst = rows + (size_t)s.variant * n + S.opt_orig[o];
                     double price = __longlong_as_double(0x7ff8000000000000LL);
                     if (bin >= 0) {
-                        const double c0 = S.opt_s0[o] * sl[swz(bin)].x;
-                        const double c1 = S.opt_s1[o] * sl[swz(bin + 1)].x;
-                        const double call = s.disc * (c0 + (c1 - c0) * S.opt_frac[o]);
-                        price = finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]);
+                        const double2 y0 = sl[swz(bin & (N - 1))];
+                        const double2 y1 = sl[swz((bin + 1) & (N - 1))];
+                        double x0 = y0.x, x1 = y1.x;
+                        if (gc.R > 1) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
+                            double sn, cs;
+                            sincospi(-2.0 * (double)(((long long)ph * bin) % gc.n_full) / (double)gc.n_full, &sn, &cs);
+                            x0 = y0.x * cs - y0.y * sn;
+                            sincospi(-2.0 * (double)(((long long)ph * (bin + 1)) % gc.n_full) / (double)gc.n_full, &sn,
+                                     &cs);
+                            x1 = y1.x * cs - y1.y * sn;
+                        }
+                        const double c0 = S.opt_s0[o] * x0;
+                        const double c1 = S.opt_s1[o] * x1;
+                        double call = s.disc * (c0 + (c1 - c0) * S.opt_frac[o]);
+                        if (ph > 0) call += *dst;
+                        price = (ph == gc.R - 1) ? finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]) : call;
                     }
-                    rows[(size_t)s.variant * n + S.opt_orig[o]] = price;
+                    *dst = price;
                 }
             }
             __syncthreads();  // slices and grp are free again
+            }
         }
         if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
     }

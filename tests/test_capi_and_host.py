@@ -131,3 +131,24 @@ def test_models_wrapper_validation_without_gpu():
         HestonParameters(-1, 0.04, 0.3, -0.7, 0.04).validate()
     p = HestonParameters(2.0, 0.04, 0.3, -0.7, 0.04)
     assert p.is_valid() and p.is_feller_satisfied() and p.to_dict()["v0"] == 0.04
+
+
+def test_population_helpers_cpu():
+    import torch
+
+    from pde_b200.calibration.population import _unpack_normal_equations, sobol_population
+
+    lb, ub = np.array([0.1, 0.01, 0.01, -0.99, 0.01]), np.array([10.0, 1.0, 2.0, 0.99, 1.0])
+    X = sobol_population(256, lb, ub, seed=42)
+    assert X.shape == (256, 5) and (X >= lb).all() and (X <= ub).all()
+    assert np.array_equal(sobol_population(128, lb, ub, seed=42, skip=128), X[128:])  # shardable by fast-forward
+    rng = np.random.default_rng(0)
+    J, r = rng.normal(size=(3, 40, 5)), rng.normal(size=(3, 40))
+    iu = np.triu_indices(5)
+    neq = np.zeros((3, 22))
+    for i in range(3):
+        neq[i, 1], neq[i, 2:7], neq[i, 7:] = r[i] @ r[i], J[i].T @ r[i], (J[i].T @ J[i])[iu]
+    rr, g, A = _unpack_normal_equations(torch.tensor(neq))
+    for i in range(3):
+        np.testing.assert_allclose(A[i].numpy(), J[i].T @ J[i], rtol=1e-13)
+        np.testing.assert_allclose(g[i].numpy(), J[i].T @ r[i], rtol=1e-13)

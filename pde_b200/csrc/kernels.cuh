@@ -308,7 +308,7 @@ __device__ __forceinline__ double finish_price(double call, bool is_call, double
 #endif
 constexpr int kNT4096 = HB_NT4096, kIL4096 = HB_IL4096, kNT512 = 128, kIL512 = 1;
 
-template <int N, int NT, int IL>
+template <int N, int NT, int IL, bool DECIM>
 __global__ void __launch_bounds__(NT, 1)
 fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
                double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int gmax,
@@ -359,7 +359,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             if (tid == 0) fill_group(grp, js, S, cls, V, t0, n_total, gmax);
             __syncthreads();
             const int count = grp.count;
-            for (int ph = 0; ph < gc.R; ++ph) {
+            const int R = DECIM ? gc.R : 1;  // DECIM = false: the plain single-transform kernel (N == Nsub)
+            for (int ph = 0; ph < R; ++ph) {
             // ---- K1: characteristic function on the damped grid -> x_j in shared memory ----
             {
                 // IL grid points per thread are evaluated side by side (IL = 1 measured best, see above).
@@ -372,7 +373,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     cplx tab[IL];
 #pragma unroll
                     for (int q = 0; q < IL; ++q) {
-                        const int j = ph + gc.R * (j0 + q * NT);  // index on the full N-point grid
+                        const int j = ph + R * (j0 + q * NT);  // index on the full N-point grid
                         v[q] = gc.eta * (double)j;
                         // Simpson weight times e^{i b v_j} = (-1)^j   
                         const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
@@ -420,7 +421,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         const double2 y0 = sl[swz(bin & (N - 1))];
                         const double2 y1 = sl[swz((bin + 1) & (N - 1))];
                         double x0 = y0.x, x1 = y1.x;
-                        if (gc.R > 1) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
+                        if (DECIM) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
                             double sn, cs;
                             sincospi(-2.0 * (double)(((long long)ph * bin) % gc.n_full) / (double)gc.n_full, &sn, &cs);
                             x0 = y0.x * cs - y0.y * sn;
@@ -432,7 +433,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         const double c1 = S.opt_s1[o] * x1;
                         double call = s.disc * (c0 + (c1 - c0) * S.opt_frac[o]);
                         if (ph > 0) call += *dst;
-                        price = (ph == gc.R - 1) ? finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]) : call;
+                        price = (ph == R - 1) ? finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]) : call;
                     }
                     *dst = price;
                 }

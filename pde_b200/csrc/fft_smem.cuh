@@ -101,6 +101,9 @@ __device__ __forceinline__ void fill_twiddles(double2* tw, int tid, int nthreads
 // barriers.  A thread owns PER = ceil((N/8)/NT) butterflies and keeps all of them in
 // registers across the barrier (the pass is in place).  LINEAR_IN: the pass reads an
 // unswizzled slice (as landed by a bulk copy) and writes the swizzled layout.
+#ifndef HB_FFT_LEAN_TWIDDLES
+#define HB_FFT_LEAN_TWIDDLES 1
+#endif
 template <int N, int NT, bool LINEAR_IN = false>
 __device__ __forceinline__ void fft_pass(double2* base, int count, int gmax, const double2* tw, int Ns, int tid) {
     constexpr int NB = N / 8;
@@ -132,11 +135,24 @@ __device__ __forceinline__ void fft_pass(double2* base, int count, int gmax, con
             if (b < NB && g < count) {
                 const int bm = b & (Ns - 1);
                 if (Ns > 1) {
+#if HB_FFT_LEAN_TWIDDLES
+                    // running power W^r: 4 live doubles instead of 14 (register budget of the fused kernel)
+                    const double2 w = tw[bm * (NB / Ns)];
+                    const cplx w1 = {w.x, w.y};
+                    cplx wp = w1;
+                    v[u][1] = cmul(v[u][1], wp);
+#pragma unroll
+                    for (int r = 2; r < 8; ++r) {
+                        wp = cmul(wp, w1);
+                        v[u][r] = cmul(v[u][r], wp);
+                    }
+#else
                     double2 w = tw[bm * (NB / Ns)];
                     cplx p[8];
                     twiddle_powers({w.x, w.y}, p);
 #pragma unroll
                     for (int r = 1; r < 8; ++r) v[u][r] = cmul(v[u][r], p[r]);
+#endif
                 }
                 dft8(v[u]);
                 const int j0 = (b - bm) * 8 + bm;

@@ -102,6 +102,11 @@ int hb_normal_eq(hb_plan* plan, const double* d_params, int ld, int P, double* d
  * (for small P: one Levenberg-Marquardt iterate). */
 int hb_jacobian(hb_plan* plan, const double* d_params, int ld, int P, double* d_res, double* d_jac, void* stream);
 
+/* Black-Scholes implied volatilities of the model prices, d_iv[p * n_opt + i]: replaces a loop of
+ * HestonModel::implied_volatility (heston.cpp:311-349; models/heston.py:313-343 builds surfaces from it).
+ * Same Newton iteration, start and clamps as the reference. */
+int hb_implied_vol(hb_plan* plan, const double* d_params, int ld, int P, double* d_iv, void* stream);
+
 /* Characteristic function phi(u_j; T_m) for every parameter set:
  * d_out[((p * n_T + m) * n_u + j) * 2 + {0,1}]; replaces HestonModel::characteristic_function
  * (heston.cpp:74-92).  d_T, d_ur, d_ui are device arrays. */
@@ -120,6 +125,7 @@ int hb_sync(void* stream);
  * as above and copies the result back before returning. */
 int hb_price_host(hb_plan* plan, const double* h_params, int P, double* h_prices);
 int hb_objective_host(hb_plan* plan, const double* h_params, int P, double* h_loss);
+int hb_implied_vol_host(hb_plan* plan, const double* h_params, int P, double* h_iv);
 int hb_normal_eq_host(hb_plan* plan, const double* h_params, int P, double* h_out);
 int hb_jacobian_host(hb_plan* plan, const double* h_params, int P, double* h_res, double* h_jac);
 

@@ -92,6 +92,9 @@ struct hb_plan {
     Bounds bd{};
     Arena surf, scratch, io_in, io_out, io_out2;
     int n_sorted = 0;
+    const double* d_strike = nullptr;    // caller-order copies for the implied-vol epilogue
+    const double* d_maturity = nullptr;
+    const uint8_t* d_is_call = nullptr;
 };
 
 namespace {
@@ -233,8 +236,11 @@ int run_host(hb_plan* pl, const double* h_params, int P, int what, double* h_out
         for (int c = 0; c < 5; ++c) pin[(size_t)c * P + p] = h_params[(size_t)p * 5 + c];
     cudaStream_t st = 0;
     HB_CUDA(cudaMemcpyAsync(pl->io_in.dev, pin, (size_t)5 * P * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = launch_jobs(pl, (const double*)pl->io_in.dev, P, P, what, (double*)pl->io_out.dev,
-                     out2_elems ? (double*)pl->io_out2.dev : nullptr, st);
+    if (what == 4)
+        rc = hb_implied_vol(pl, (const double*)pl->io_in.dev, P, P, (double*)pl->io_out.dev, st);
+    else
+        rc = launch_jobs(pl, (const double*)pl->io_in.dev, P, P, what, (double*)pl->io_out.dev,
+                         out2_elems ? (double*)pl->io_out2.dev : nullptr, st);
     if (rc) return rc;
     HB_CUDA(cudaMemcpyAsync(pl->io_out.pinned, pl->io_out.dev, out_elems * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (out2_elems)
@@ -341,6 +347,8 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
         return fail(HB_ERR_INVALID_ARGUMENT, "NULL option arrays");
     DeviceGuard guard(pl->device);
     if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    // launches of this plan may still be reading the old tables on a caller stream
+    HB_CUDA(cudaDeviceSynchronize());
     const double nan = std::numeric_limits<double>::quiet_NaN();
     const int N = pl->N;
     const double alpha = pl->alpha, eta = pl->eta;
@@ -431,6 +439,9 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                  o_s1 = bb.add(opt_s1), o_lnk = bb.add(opt_lnk), o_kd = bb.add(opt_kdisc), o_call = bb.add(opt_call),
                  o_noff = bb.add(need_off), o_nq = bb.add(need_q), o_io = bb.add(intr_orig), o_iv = bb.add(intr_val),
                  o_mkt = bb.add(mkt);
+    const size_t o_K = bb.add(std::vector<double>(strike, strike + n_opt)),
+                 o_Tm = bb.add(std::vector<double>(maturity, maturity + n_opt)),
+                 o_ic = bb.add(std::vector<uint8_t>(is_call, is_call + n_opt));
     pl->surf.want_pinned = true;
     int rc = pl->surf.reserve(bb.bytes.size());
     if (rc) return rc;
@@ -463,6 +474,9 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     S.intr_orig = (const int*)(base + o_io);
     S.intr_val = (const double*)(base + o_iv);
     S.mkt_orig = (const double*)(base + o_mkt);
+    pl->d_strike = (const double*)(base + o_K);
+    pl->d_maturity = (const double*)(base + o_Tm);
+    pl->d_is_call = (const uint8_t*)(base + o_ic);
     pl->n_sorted = (int)opt_orig.size();
     pl->has_surface = true;
     pl->has_market = market != nullptr;
@@ -480,6 +494,20 @@ int hb_normal_eq(hb_plan* pl, const double* d_params, int ld, int P, double* d_o
 }
 int hb_jacobian(hb_plan* pl, const double* d_params, int ld, int P, double* d_res, double* d_jac, void* stream) {
     return launch_jobs(pl, d_params, ld, P, W_JAC, d_res, d_jac, (cudaStream_t)stream);
+}
+
+int hb_implied_vol(hb_plan* pl, const double* d_params, int ld, int P, double* d_iv, void* stream) {
+    int rc = launch_jobs(pl, d_params, ld, P, W_PRICE, d_iv, nullptr, (cudaStream_t)stream);  // prices, in place
+    if (rc || P == 0 || pl->S.n_opt == 0) return rc;
+    DeviceGuard guard(pl->device);
+    const size_t total = (size_t)P * pl->S.n_opt;
+    const int block = 128, grid = (int)std::min<size_t>((total + block - 1) / block, (size_t)pl->sm_count * 16);
+    implied_vol_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_iv, d_params, ld, P, pl->S.n_opt, pl->d_strike,
+                                                                 pl->d_maturity, pl->d_is_call, pl->S.spot, pl->S.rate,
+                                                                 pl->S.dividend, d_iv);
+    g_launches++;
+    HB_CUDA(cudaGetLastError());
+    return HB_OK;
 }
 
 int hb_cf(const double* d_params, int ld, int P, const double* d_T, int n_T, const double* d_ur, const double* d_ui,
@@ -531,6 +559,10 @@ int hb_sync(void* stream) {
 int hb_price_host(hb_plan* pl, const double* h_params, int P, double* h_prices) {
     const size_t n = pl && pl->has_surface ? (size_t)pl->S.n_opt : 0;
     return run_host(pl, h_params, P, W_PRICE, h_prices, (size_t)P * n, nullptr, 0);
+}
+int hb_implied_vol_host(hb_plan* pl, const double* h_params, int P, double* h_iv) {
+    const size_t n = pl && pl->has_surface ? (size_t)pl->S.n_opt : 0;
+    return run_host(pl, h_params, P, 4 /* W_PRICE + implied-vol epilogue */, h_iv, (size_t)P * n, nullptr, 0);
 }
 int hb_objective_host(hb_plan* pl, const double* h_params, int P, double* h_loss) {
     return run_host(pl, h_params, P, W_LOSS, h_loss, (size_t)P, nullptr, 0);

@@ -577,6 +577,54 @@ refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restri
 }
 
 // ============================================================================================
+// Black-Scholes implied volatility of model prices: HestonModel::implied_volatility,
+// heston.cpp:311-349 (Newton from sqrt(v0), tol 1e-8, <= 100 steps, vol in [0.001, 5],
+// vega < 1e-12 -> vol *= 1.5), with black_scholes_price / _vega of heston.cpp:275-309.
+// One thread per (parameter set, option); prices come from hb_price.  Not a hot path: libdevice math.
+// ============================================================================================
+
+__device__ __forceinline__ double bs_norm_cdf(double x) { return 0.5 * (1.0 + erf(x / sqrt(2.0))); }  // :16-18
+
+__global__ void implied_vol_kernel(const double* __restrict__ prices, const double* __restrict__ params, int ld, int P,
+                                   int n, const double* __restrict__ strike, const double* __restrict__ maturity,
+                                   const uint8_t* __restrict__ is_call, double spot, double rate, double dividend,
+                                   double* __restrict__ out) {
+    const size_t total = (size_t)P * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % n), p = (int)(idx / n);
+        const double target = prices[idx], K = strike[i], T = maturity[i];
+        const bool call = is_call[i] != 0;
+        double vol = sqrt(params[(size_t)4 * ld + p]);  // sqrt(v0)
+        if (target != target) {
+            out[idx] = target;  // invalid option / parameter set
+            continue;
+        }
+        if (T <= 0.0) {  // :316-318
+            out[idx] = 0.0;
+            continue;
+        }
+        const double fwd = spot * exp((rate - dividend) * T), disc = exp(-rate * T), sq = sqrt(T);
+        const double sdiv = spot * exp(-dividend * T);
+        for (int it = 0; it < 100; ++it) {
+            const double vs = vol * sq;
+            const double d1 = (log(fwd / K) + 0.5 * vol * vol * T) / vs, d2 = d1 - vs;
+            const double bs = call ? sdiv * bs_norm_cdf(d1) - K * disc * bs_norm_cdf(d2)
+                                   : K * disc * bs_norm_cdf(-d2) - sdiv * bs_norm_cdf(-d1);
+            const double vega = (vol <= 0.0) ? 0.0 : sdiv * sq * 0.3989422804014327 * exp(-0.5 * d1 * d1);
+            if (vega < 1e-12) {
+                vol *= 1.5;
+                continue;
+            }
+            const double diff = bs - target;
+            if (fabs(diff) < 1e-8) break;
+            vol = fmax(0.001, fmin(5.0, vol - diff / vega));
+        }
+        out[idx] = vol;
+    }
+}
+
+// ============================================================================================
 // K1 alone: characteristic function for arbitrary complex u
 // ============================================================================================
 

@@ -94,12 +94,18 @@ class HestonModel:
     def implied_volatility_surface(self, strikes, maturities, spot: float, rate: float,
                                    dividend: float = 0.0) -> np.ndarray:
         """(strikes x maturities) matrix of call implied vols (models/heston.py:313-343)."""
-        strikes, maturities = np.asarray(strikes), np.asarray(maturities)
-        surface = np.zeros((len(strikes), len(maturities)))
-        for i, K in enumerate(strikes):
-            for j, T in enumerate(maturities):
-                surface[i, j] = self.implied_volatility(K, T, spot, rate, dividend, is_call=True)
-        return surface
+        # the reference loops over implied_volatility per (K, T); one batched launch gives the same numbers
+        from ..pricer import BatchPricer
+
+        strikes, maturities = np.asarray(strikes, dtype=np.float64), np.asarray(maturities, dtype=np.float64)
+        K = np.repeat(strikes, len(maturities))
+        T = np.tile(maturities, len(strikes))
+        p = self.params
+        pricer = BatchPricer("refgrid", device=quant_cpp._DEVICE).set_surface(K, T, True, None, S0=spot, r=rate,
+                                                                              q=dividend)
+        iv = pricer.implied_vol_host(np.array([[p.kappa, p.theta, p.sigma, p.rho, p.v0]]))[0]
+        pricer.close()
+        return iv.reshape(len(strikes), len(maturities))
 
     @classmethod
     def from_dict(cls, params: Dict[str, float]) -> "HestonModel":

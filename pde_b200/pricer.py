@@ -131,6 +131,17 @@ class BatchPricer:
         check(self._L.hb_objective(self._h, soa.data_ptr(), P, P, out.data_ptr(), st))
         return out
 
+    def implied_vol(self, params):
+        """[P, 5] -> Black-Scholes implied vols of the model prices [P, n_options]
+        (batched HestonModel::implied_volatility, heston.cpp:311-349)."""
+        import torch
+
+        soa, st = self._soa(params)
+        P = soa.shape[1]
+        out = torch.empty((P, self.n_options), dtype=torch.float64, device=params.device)
+        check(self._L.hb_implied_vol(self._h, soa.data_ptr(), P, P, out.data_ptr(), st))
+        return out
+
     def normal_equations(self, params):
         """[P, 5] -> [P, 22] = loss, ||r||^2, J^T r (5), triu(J^T J) (15)."""
         import torch
@@ -157,6 +168,12 @@ class BatchPricer:
         x = _np_d(np.atleast_2d(params))
         out = np.empty((x.shape[0], self.n_options))
         check(self._L.hb_price_host(self._h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def implied_vol_host(self, params) -> np.ndarray:
+        x = _np_d(np.atleast_2d(params))
+        out = np.empty((x.shape[0], self.n_options))
+        check(self._L.hb_implied_vol_host(self._h, _ptr(x), x.shape[0], _ptr(out)))
         return out
 
     def objective_host(self, params) -> np.ndarray:

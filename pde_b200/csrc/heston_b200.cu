@@ -171,13 +171,13 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
         const size_t smem = fft_smem_bytes(pl->Nsub, gmax);
         if (pl->Nsub == 4096) {
             if (pl->R == 1)
-                fft_job_kernel<4096, kNT4096, kIL4096, false><<<grid, kNT4096, smem, st>>>(
+                fft_job_kernel<4096, kNT4096, false><<<grid, kNT4096, smem, st>>>(
                     S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0);
             else
-                fft_job_kernel<4096, kNT4096, kIL4096, true><<<grid, kNT4096, smem, st>>>(
+                fft_job_kernel<4096, kNT4096, true><<<grid, kNT4096, smem, st>>>(
                     S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0);
         } else {
-            fft_job_kernel<512, kNT512, kIL512, false><<<grid, kNT512, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
+            fft_job_kernel<512, kNT512, false><<<grid, kNT512, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
                                                              scratch, gmax, split ? 1 : 0);
         }
         g_launches++;
@@ -304,9 +304,9 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     std::memcpy(pl->bd.lb, lb, sizeof lb);
     std::memcpy(pl->bd.ub, ub, sizeof ub);
     if (mode == HB_MODE_FFT) {
-        int rc = (n_grid > 4096)    ? set_smem(fft_job_kernel<4096, kNT4096, kIL4096, true>, fft_smem_bytes(4096, gmax_for(4096)))
-                 : (n_grid == 4096) ? set_smem(fft_job_kernel<4096, kNT4096, kIL4096, false>, fft_smem_bytes(4096, gmax_for(4096)))
-                                    : set_smem(fft_job_kernel<512, kNT512, kIL512, false>, fft_smem_bytes(512, gmax_for(512)));
+        int rc = (n_grid > 4096)    ? set_smem(fft_job_kernel<4096, kNT4096, true>, fft_smem_bytes(4096, gmax_for(4096)))
+                 : (n_grid == 4096) ? set_smem(fft_job_kernel<4096, kNT4096, false>, fft_smem_bytes(4096, gmax_for(4096)))
+                                    : set_smem(fft_job_kernel<512, kNT512, false>, fft_smem_bytes(512, gmax_for(512)));
         if (rc) {
             delete pl;
             return rc;

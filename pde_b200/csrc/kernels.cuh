@@ -296,19 +296,15 @@ __device__ __forceinline__ double finish_price(double call, bool is_call, double
 // Fused Carr-Madan FFT job kernel
 // ============================================================================================
 
-// Launch shapes of the fused kernel (threads per CTA, grid points interleaved per thread).
+// Threads per CTA of the fused kernel.  Measured on B200 (profiles/r01_shape_sweep.txt): 512 threads
+// x 128 registers is the knee -- 640/768/1024 threads spill or idle (4096 points do not tile) and are
+// 3-25 % slower; interleaving 2 or 4 grid points per thread does not fit the register file.
 #ifndef HB_NT4096
 #define HB_NT4096 512
 #endif
-// Measured on B200 (slices/s at 4736 sets, profiles/r01_shape_sweep.txt): 512x1 11.78 M,
-// 640x1 11.43 M, 512x2 11.22 M, 768x1 10.68 M, 256x2 10.62 M, 256x4 9.88 M, 1024x1 9.80 M --
-// 128 registers/thread is the knee: more warps spill, explicit interleave does not fit.
-#ifndef HB_IL4096
-#define HB_IL4096 1
-#endif
-constexpr int kNT4096 = HB_NT4096, kIL4096 = HB_IL4096, kNT512 = 128, kIL512 = 1;
+constexpr int kNT4096 = HB_NT4096, kNT512 = 128;
 
-template <int N, int NT, int IL, bool DECIM>
+template <int N, int NT, bool DECIM>
 __global__ void __launch_bounds__(NT, 1)
 fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
                double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int gmax,
@@ -379,43 +375,36 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             }
             for (int ph = 0; ph < R; ++ph) {
             // ---- K1: characteristic function on the damped grid -> x_j in shared memory ----
+            // One grid point per thread at a time: interleaving points explicitly was measured slower
+            // (profiles/r01_shape_sweep.txt); the ILP comes from the interleaved chains inside stage B / F.
             {
                 const ClassConst cc = grp.cc;
-                static_assert(IL == 1, "one grid point per thread at a time (explicit interleave measured slower)");
 #pragma unroll 1
                 for (int k = 0, j0 = tid; j0 < N; ++k, j0 += NT) {
-                    double v[IL];
-                    StageA a[IL];
-                    cplx tab[IL];
-                    {
-                        constexpr int q = 0;
-                        const int j = ph + R * j0;  // index on the full N-point grid
-                        v[q] = gc.eta * (double)j;
-                        if (DECIM) {
-                            // Simpson weight times e^{i b v_j} = (-1)^j   
-                            const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
-                            a[q] = stage_a_tab(cc, v[q], gc.ui, gc.alpha, wgt, &tab[q]);
-                        } else {
-                            a[q] = ac[k];
-                            tab[q] = tabc[k];
-                        }
+                    const int j = ph + R * j0;  // index on the full N-point grid
+                    const double v = gc.eta * (double)j;
+                    StageA a;
+                    cplx tab;
+                    if (DECIM) {
+                        // Simpson weight times e^{i b v_j} = (-1)^j   
+                        const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
+                        a = stage_a_tab(cc, v, gc.ui, gc.alpha, wgt, &tab);
+                    } else {
+                        a = ac[k];
+                        tab = tabc[k];
                     }
-                    StageB b[IL] = {};
+                    StageB b = {};
                     double Tprev = -1.0;
 #pragma unroll 1
                     for (int g = 0; g < count; ++g) {
                         const SubSlice& s = grp.s[g];
-                        if (s.T != Tprev) {
-#pragma unroll
-                            for (int q = 0; q < IL; ++q) b[q] = stage_b(a[q], s.T);
+                        if (s.T != Tprev) {  // slices of one maturity (base, theta', v0') share stage B
+                            b = stage_b(a, s.T);
                             Tprev = s.T;
                         }
                         const SliceConst sc = {s.kts, s.v0s, s.lsm};
-#pragma unroll
-                        for (int q = 0; q < IL; ++q) {
-                            const cplx phi = stage_f(b[q], sc, v[q], gc.ui);
-                            sts_c(slices + (size_t)g * N, j0 + q * NT, cmul(phi, tab[q]));
-                        }
+                        const cplx phi = stage_f(b, sc, v, gc.ui);
+                        sts_c(slices + (size_t)g * N, j0, cmul(phi, tab));
                     }
                 }
             }

@@ -90,7 +90,7 @@ struct hb_plan {
     bool has_surface = false, has_market = false;
     SurfaceDev S{};
     Bounds bd{};
-    Arena surf, scratch, io_in, io_out, io_out2;
+    Arena surf, scratch, io_in, io_out, io_out2, ctr;
     int n_sorted = 0;
     const double* d_strike = nullptr;    // caller-order copies for the implied-vol epilogue
     const double* d_maturity = nullptr;
@@ -152,6 +152,13 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
     const int n = S.n_opt, M = S.n_mat, V = (what >= W_NEQ) ? 6 : 1;
     GridConst gc = {pl->eta, pl->alpha, -(pl->alpha + 1.0), pl->eta / 3.0, pl->R, pl->N};
     const size_t row_bytes = (size_t)6 * std::max(n, 1) * sizeof(double);
+    // dynamic job queue: one counter per plan, reset in stream order before each launch
+    {
+        int rc = pl->ctr.reserve(sizeof(unsigned long long));
+        if (rc) return rc;
+        HB_CUDA(cudaMemsetAsync(pl->ctr.dev, 0, sizeof(unsigned long long), st));
+    }
+    unsigned long long* ctr = (unsigned long long*)pl->ctr.dev;
 
     if (pl->mode == HB_MODE_FFT) {
         const int gmax = gmax_for(pl->Nsub);
@@ -172,13 +179,13 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
         if (pl->Nsub == 4096) {
             if (pl->R == 1)
                 fft_job_kernel<4096, kNT4096, false><<<grid, kNT4096, smem, st>>>(
-                    S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0);
+                    S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0, ctr);
             else
                 fft_job_kernel<4096, kNT4096, true><<<grid, kNT4096, smem, st>>>(
-                    S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0);
+                    S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0, ctr);
         } else {
             fft_job_kernel<512, kNT512, false><<<grid, kNT512, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
-                                                             scratch, gmax, split ? 1 : 0);
+                                                             scratch, gmax, split ? 1 : 0, ctr);
         }
         g_launches++;
         HB_CUDA(cudaGetLastError());
@@ -204,7 +211,7 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
             scratch = (double*)pl->scratch.dev;
         }
         refgrid_job_kernel<256><<<grid, 256, 0, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch,
-                                                      split ? 1 : 0);
+                                                      split ? 1 : 0, ctr);
         g_launches++;
         HB_CUDA(cudaGetLastError());
         if (split && what != W_PRICE) {
@@ -321,6 +328,7 @@ int hb_plan_destroy(hb_plan* pl) {
     DeviceGuard guard(pl->device);
     pl->surf.release();
     pl->scratch.release();
+    pl->ctr.release();
     pl->io_in.release();
     pl->io_out.release();
     pl->io_out2.release();

@@ -308,7 +308,7 @@ template <int N, int NT, bool DECIM>
 __global__ void __launch_bounds__(NT, 1)
 fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
                double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int gmax,
-               int split) {
+               int split, unsigned long long* job_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* slices = reinterpret_cast<double2*>(smem_raw);
     double2* tw = slices + (size_t)gmax * N;
@@ -333,7 +333,18 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     StageA ac[PTS];
     cplx tabc[PTS];
 
-    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    // Jobs differ in cost (decayed tails take the short path of stage F), so after its first,
+    // statically assigned job a CTA pulls the next one from a global counter.
+    __shared__ long long s_job;
+    auto next_job = [&](long long cur) -> long long {
+        if (!job_counter) return cur + gridDim.x;
+        __syncthreads();
+        if (tid == 0) s_job = (long long)gridDim.x + (long long)atomicAdd(job_counter, 1ULL);
+        __syncthreads();
+        return s_job;
+    };
+
+    for (long long job = blockIdx.x; job < n_jobs; job = next_job(job)) {
         const int p = split ? (int)(job / groups_per_set) : (int)job;
         const int gi_begin = split ? (int)(job % groups_per_set) : 0;
         const int gi_end = split ? gi_begin + 1 : groups_per_set;
@@ -488,8 +499,10 @@ constexpr int kRefPoints = 1024;  // heston.cpp:126
 template <int NT>
 __global__ void __launch_bounds__(NT, 2)
 refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
-                   double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int split) {
+                   double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int split,
+                   unsigned long long* job_counter) {
     __shared__ double2 psi[kRefPoints];
+    __shared__ long long s_job;
     __shared__ JobState js;
     __shared__ double red[(NT / 32) * 23];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -499,7 +512,14 @@ refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restri
     const int slices_per_set = V * M;
     const long long n_jobs = split ? (long long)P * slices_per_set : (long long)P;
 
-    for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    auto next_job = [&](long long cur) -> long long {  // dynamic queue, as in fft_job_kernel
+        if (!job_counter) return cur + gridDim.x;
+        __syncthreads();
+        if (tid == 0) s_job = (long long)gridDim.x + (long long)atomicAdd(job_counter, 1ULL);
+        __syncthreads();
+        return s_job;
+    };
+    for (long long job = blockIdx.x; job < n_jobs; job = next_job(job)) {
         const int p = split ? (int)(job / slices_per_set) : (int)job;
         const int si_begin = split ? (int)(job % slices_per_set) : 0;
         const int si_end = split ? si_begin + 1 : slices_per_set;

@@ -332,6 +332,11 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     constexpr int PTS = DECIM ? 1 : (N + NT - 1) / NT;  // grid points owned by one thread
     StageA ac[PTS];
     cplx tabc[PTS];
+    // dead[k] bit m: the base set's phi at this thread's k-th point and maturity m has underflowed with
+    // a wide margin (see K1).  Only available when one CTA prices all classes of a set.
+    constexpr int kDeadWords = 4;
+    unsigned int dead[PTS][kDeadWords];
+    const bool track_tail = !DECIM && !split && V > 1 && M <= 32 * kDeadWords;
 
     // Jobs differ in cost (decayed tails take the short path of stage F), so after its first,
     // statically assigned job a CTA pulls the next one from a global counter.
@@ -349,6 +354,12 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
         const int gi_begin = split ? (int)(job % groups_per_set) : 0;
         const int gi_end = split ? gi_begin + 1 : groups_per_set;
         int cached_cls = -1;  // class whose stage A sits in ac[]
+        if (track_tail) {
+#pragma unroll
+            for (int k = 0; k < PTS; ++k)
+#pragma unroll
+                for (int w = 0; w < kDeadWords; ++w) dead[k][w] = 0u;
+        }
         __syncthreads();  // previous job's finalize has consumed rows/js
         if (tid == 0) job_setup(js, params, ld, p, bd, V);
         __syncthreads();
@@ -394,6 +405,21 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 for (int k = 0, j0 = tid; j0 < N; ++k, j0 += NT) {
                     const int j = ph + R * j0;  // index on the full N-point grid
                     const double v = gc.eta * (double)j;
+                    // Decayed tail of a perturbed class: where the base set's log|phi| is below -800 the
+                    // kappa'/sigma'/rho' slice (parameters moved by 1.5e-8 relative) is exactly 0 as well --
+                    // the exponent would have to move by 54, i.e. a condition number above 4e6; measured
+                    // over the box it is below 200 (tests/test_host_math.py).  Skip stage B and F there.
+                    if (track_tail && cls != 0) {
+                        bool any_live = false;
+                        for (int g = 0; g < count; ++g) {
+                            const int m = grp.s[g].mat;
+                            any_live |= !((dead[k][m >> 5] >> (m & 31)) & 1u);
+                        }
+                        if (!any_live) {
+                            for (int g = 0; g < count; ++g) sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
+                            continue;
+                        }
+                    }
                     StageA a;
                     cplx tab;
                     if (DECIM) {
@@ -409,12 +435,18 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
 #pragma unroll 1
                     for (int g = 0; g < count; ++g) {
                         const SubSlice& s = grp.s[g];
+                        if (track_tail && cls != 0 && ((dead[k][s.mat >> 5] >> (s.mat & 31)) & 1u)) {
+                            sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
+                            continue;
+                        }
                         if (s.T != Tprev) {  // slices of one maturity (base, theta', v0') share stage B
                             b = stage_b(a, s.T);
                             Tprev = s.T;
                         }
                         const SliceConst sc = {s.kts, s.v0s, s.lsm};
-                        const cplx phi = stage_f(b, sc, v, gc.ui);
+                        double er;
+                        const cplx phi = stage_f(b, sc, v, gc.ui, &er);
+                        if (track_tail && s.variant == 0 && er < -800.0) dead[k][s.mat >> 5] |= 1u << (s.mat & 31);
                         sts_c(slices + (size_t)g * N, j0, cmul(phi, tab));
                     }
                 }

@@ -33,3 +33,16 @@ extern "C" void hm_cexp(int n, const double* x, const double* y, double* re, dou
 extern "C" void hm_clog1p(int n, const double* dr, const double* di, const double* w, double* lg, double* ar, double* rw) {
     for (int i = 0; i < n; ++i) hb::clog1p_rcp_nb(dr[i], di[i], w[i], lg + i, ar + i, rw + i);
 }
+
+// log|phi| (the real part of the CF exponent) on a grid: used to study how far the exponent of a
+// finite-difference-perturbed parameter set can move away from the base set's (tail-skip margin).
+extern "C" void hm_cf_exponent(const double* p, int n, const double* ur, double ui, double T, double S0, double r,
+                               double q, double* er) {
+    hb::ClassConst c = {p[0], p[2] * p[2], p[3] * p[2]};
+    hb::SliceConst s = {p[0] * p[1] / c.sigma2, p[4] / c.sigma2, log(S0) + (r - q) * T};
+    for (int j = 0; j < n; ++j) {
+        hb::StageA a = hb::stage_a(c, ur[j], ui);
+        hb::StageB b = hb::stage_b(a, T);
+        hb::stage_f(b, s, ur[j], ui, er + j);
+    }
+}

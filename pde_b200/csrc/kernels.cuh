@@ -334,9 +334,12 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     cplx tabc[PTS];
     // dead[k] bit m: the base set's phi at this thread's k-th point and maturity m has underflowed with
     // a wide margin (see K1).  Only available when one CTA prices all classes of a set.
-    constexpr int kDeadWords = 4;
-    unsigned int dead[PTS][kDeadWords];
-    const bool track_tail = !DECIM && !split && V > 1 && M <= 32 * kDeadWords;
+    constexpr int kDeadWords = 2;  // 128 maturities
+    unsigned long long dead[PTS][kDeadWords];
+#ifndef HB_TAIL
+#define HB_TAIL 1
+#endif
+    const bool track_tail = HB_TAIL && !DECIM && !split && V > 1 && M <= 64 * kDeadWords;
 
     // Jobs differ in cost (decayed tails take the short path of stage F), so after its first,
     // statically assigned job a CTA pulls the next one from a global counter.
@@ -354,11 +357,12 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
         const int gi_begin = split ? (int)(job % groups_per_set) : 0;
         const int gi_end = split ? gi_begin + 1 : groups_per_set;
         int cached_cls = -1;  // class whose stage A sits in ac[]
+        int job_has_dead = -1;  // -1: not known yet (class 0 still running)
         if (track_tail) {
 #pragma unroll
             for (int k = 0; k < PTS; ++k)
 #pragma unroll
-                for (int w = 0; w < kDeadWords; ++w) dead[k][w] = 0u;
+                for (int w = 0; w < kDeadWords; ++w) dead[k][w] = 0ull;
         }
         __syncthreads();  // previous job's finalize has consumed rows/js
         if (tid == 0) job_setup(js, params, ld, p, bd, V);
@@ -380,7 +384,15 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             const int n_total = (V > 1 && cls == 0) ? 3 * M : M;
             const int t0 = ((gi < g0) ? gi : (gi - g0) % g1) * gmax;
             if (tid == 0) fill_group(grp, js, S, cls, V, t0, n_total, gmax);
-            __syncthreads();
+            if (track_tail && cls != 0 && job_has_dead < 0) {
+                // class 0 is done: does any thread of the CTA hold a decayed point?  (block-uniform)
+                unsigned long long any = 0ull;
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) any |= dead[k][0] | dead[k][1];
+                job_has_dead = __syncthreads_or(any != 0ull);
+            } else {
+                __syncthreads();
+            }
             const int count = grp.count;
             const int R = DECIM ? gc.R : 1;  // DECIM = false: the plain single-transform kernel (N == Nsub)
             // Stage A (and the Carr-Madan weight) depends on the class and the grid point only: compute it
@@ -401,24 +413,30 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             // (profiles/r01_shape_sweep.txt); the ILP comes from the interleaved chains inside stage B / F.
             {
                 const ClassConst cc = grp.cc;
+                // Decayed tail of a perturbed class: where the base set's log|phi| is below -800 the
+                // kappa'/sigma'/rho' slice (parameters moved by 1.5e-8 relative) is exactly 0 as well --
+                // the exponent would have to move by 54, i.e. a condition number above 4e6; measured
+                // over the box it is below 200 (tests/test_host_math.py).  Points where every slice of
+                // the group is dead skip stage B and F.  skip bit k <-> this thread's k-th point.
+                unsigned skip = 0u;
+                if (track_tail && cls != 0 && job_has_dead) {
+                    const int m0 = grp.s[0].mat;  // a perturbed class walks maturities in order: slice g = m0 + g
+                    const unsigned long long want = (1ull << count) - 1ull;
+#pragma unroll
+                    for (int k = 0; k < PTS; ++k) {
+                        const unsigned long long lo = dead[k][0], hi = dead[k][1];
+                        const unsigned long long bits =
+                            (m0 < 64) ? ((lo >> m0) | (m0 ? (hi << (64 - m0)) : 0ull)) : (hi >> (m0 - 64));
+                        skip |= ((bits & want) == want ? 1u : 0u) << k;
+                    }
+                }
 #pragma unroll 1
                 for (int k = 0, j0 = tid; j0 < N; ++k, j0 += NT) {
                     const int j = ph + R * j0;  // index on the full N-point grid
                     const double v = gc.eta * (double)j;
-                    // Decayed tail of a perturbed class: where the base set's log|phi| is below -800 the
-                    // kappa'/sigma'/rho' slice (parameters moved by 1.5e-8 relative) is exactly 0 as well --
-                    // the exponent would have to move by 54, i.e. a condition number above 4e6; measured
-                    // over the box it is below 200 (tests/test_host_math.py).  Skip stage B and F there.
-                    if (track_tail && cls != 0) {
-                        bool any_live = false;
-                        for (int g = 0; g < count; ++g) {
-                            const int m = grp.s[g].mat;
-                            any_live |= !((dead[k][m >> 5] >> (m & 31)) & 1u);
-                        }
-                        if (!any_live) {
-                            for (int g = 0; g < count; ++g) sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
-                            continue;
-                        }
+                    if ((skip >> k) & 1u) {
+                        for (int g = 0; g < count; ++g) sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
+                        continue;
                     }
                     StageA a;
                     cplx tab;
@@ -435,10 +453,6 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
 #pragma unroll 1
                     for (int g = 0; g < count; ++g) {
                         const SubSlice& s = grp.s[g];
-                        if (track_tail && cls != 0 && ((dead[k][s.mat >> 5] >> (s.mat & 31)) & 1u)) {
-                            sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
-                            continue;
-                        }
                         if (s.T != Tprev) {  // slices of one maturity (base, theta', v0') share stage B
                             b = stage_b(a, s.T);
                             Tprev = s.T;
@@ -446,7 +460,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         const SliceConst sc = {s.kts, s.v0s, s.lsm};
                         double er;
                         const cplx phi = stage_f(b, sc, v, gc.ui, &er);
-                        if (track_tail && s.variant == 0 && er < -800.0) dead[k][s.mat >> 5] |= 1u << (s.mat & 31);
+                        if (track_tail && s.variant == 0 && er < -800.0) dead[k][s.mat >> 6] |= 1ull << (s.mat & 63);
                         sts_c(slices + (size_t)g * N, j0, cmul(phi, tab));
                     }
                 }

@@ -164,25 +164,124 @@ __device__ __forceinline__ void fft_pass(double2* base, int count, int gmax, con
     if (gmax == 1) __syncthreads();  // a lone slice has no neighbour barrier to fence its stores
 }
 
-// Last pass (Ns = N/8) only for the butterflies q in need_q[0..n_need): outputs land in
-// place at slots q + r N/8.  No barrier inside; the caller syncs before and after.
-template <int N, int NT>
-__device__ __forceinline__ void fft_last_pass_pruned(double2* s, const double2* tw, const int* need_q, int n_need,
-                                                     int tid) {
-    constexpr int NB = N / 8;
-    for (int t = tid; t < n_need; t += NT) {
-        const int q = need_q[t];
-        double2 w = tw[q];
-        cplx p[8], v[8];
-        twiddle_powers({w.x, w.y}, p);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = lds_c(s, q + r * NB);
-#pragma unroll
-        for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], p[r]);
-        dft8(v);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) sts_c(s, q + r * NB, v[bitrev3(r)]);
+// ================================================================================================
+// In-place decimation-in-frequency transform of the fused kernel (N = 8^L).
+//
+// Carr-Madan reads Re X_m only at the few bins bracketing the quoted strikes (a window of ~70
+// consecutive m for strikes 80..120 at N = 4096).  A decimation-in-FREQUENCY factorisation prunes
+// that much better than the autosort DIT passes above: pass i (stride S = N/8^i) resolves digit
+// m_{i-1} of the output index m = m_0 + 8 m_1 + 64 m_2 + ..., so
+//   * the passes are in place on the thread's own 8 slots -- no load/barrier/store split, one
+//     barrier per pass for all slices of a group, and the FIRST pass needs no barrier at all
+//     because butterfly `tid` reads exactly the points tid + r N/8 that thread `tid` wrote in K1;
+//   * the second-to-last pass (S = 8) only forms the outputs whose digit m_{L-2} occurs in the
+//     window (fmask, typically 2 of 8) -- one twiddle product per kept output instead of 7;
+//   * the last pass (S = 1) is not a pass: the interpolation epilogue evaluates the single output
+//     X_m = sum_r y[pos(m) + r] w8^{r m_{L-1}} it needs (dif_bin).
+// X_m ends up at the digit-reversed position pos(m) = m_0 8^{L-1} + m_1 8^{L-2} + ... + m_{L-1}.
+// Twiddles: the first pass of a grid above 512 points multiplies output f by W_N^{t f}, formed as
+// running powers of W_N^t (table tw, N/8 entries); every later pass has 8 S <= 512 and reads
+// W_{8S}^{t f} = W_512^{t f 512/(8S)} directly from a 512-entry table (tw512), which moves work
+// from the FP64 pipe (the binding one) to the idle LSU.
+// ================================================================================================
+
+template <int N>
+struct Log8 {
+    static constexpr int value = 1 + Log8<N / 8>::value;
+};
+template <>
+struct Log8<1> {
+    static constexpr int value = 0;
+};
+
+__device__ __forceinline__ void fill_tw512(double2* t512, int tid, int nthreads) {
+    for (int k = tid; k < 512; k += nthreads) {
+        double sn, cs;
+        sincospi(-(double)k / 256.0, &sn, &cs);
+        t512[k] = make_double2(cs, sn);
     }
+}
+
+// One DIF pass with stride S over slices g < count.  MASKED: only outputs f with bit f of fmask[g] set
+// are formed (the others are never read again).
+template <int N, int NT, int S, bool MASKED>
+__device__ __forceinline__ void dif_pass(double2* base, int count, const double2* tw, const double2* tw512,
+                                         const unsigned* fmask, int tid) {
+    constexpr int NB = N / 8;
+    constexpr int PER = (NB + NT - 1) / NT;
+    static_assert(NB % NT == 0 || NB < NT, "butterflies must tile over the block");
+    constexpr bool RUNNING = (8 * S == N) && (N > 512);
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int b = tid + u * NT;
+        if (b < NB) {
+            const int t = b & (S - 1);
+            const int p0 = ((b - t) << 3) + t;
+#pragma unroll 1
+            for (int g = 0; g < count; ++g) {
+                double2* sl = base + (size_t)g * N;
+                const unsigned keep = MASKED ? fmask[g] : 0xffu;
+                cplx v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[r] = lds_c(sl, p0 + r * S);
+                dft8(v);  // X_f in v[bitrev3(f)]
+                if (RUNNING) {
+                    const double2 w = tw[t];
+                    const cplx w1 = {w.x, w.y};
+                    cplx wp = w1;
+                    v[bitrev3(1)] = cmul(v[bitrev3(1)], wp);
+#pragma unroll
+                    for (int f = 2; f < 8; ++f) {
+                        wp = cmul(wp, w1);
+                        v[bitrev3(f)] = cmul(v[bitrev3(f)], wp);
+                    }
+                } else {
+                    constexpr int STEP = 512 / (8 * S);
+#pragma unroll
+                    for (int f = 1; f < 8; ++f) {
+                        if (!MASKED || ((keep >> f) & 1u)) {
+                            const double2 w = tw512[(t * f * STEP) & 511];
+                            v[bitrev3(f)] = cmul(v[bitrev3(f)], {w.x, w.y});
+                        }
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < 8; ++f)
+                    if (!MASKED || ((keep >> f) & 1u)) sts_c(sl, p0 + f * S, v[bitrev3(f)]);
+            }
+        }
+    }
+}
+
+// Digit of m resolved by the masked (S = 8) pass, and the position of X_m's last-pass inputs.
+template <int N>
+__host__ __device__ constexpr int dif_mask_digit(int m) {
+    return (m >> (3 * (Log8<N>::value - 2))) & 7;
+}
+template <int N>
+__device__ __forceinline__ int dif_pos(int m) {
+    constexpr int L = Log8<N>::value;
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < L - 1; ++i) p |= ((m >> (3 * i)) & 7) << (3 * (L - 1 - i));
+    return p;
+}
+
+// X_m of a slice that went through every pass down to S = 8: the one needed output of its last
+// radix-8 butterfly.  w8^k = W_512^{64 k}.  WANT_IM = false returns Re X_m only (im = 0).
+template <int N, bool WANT_IM>
+__device__ __forceinline__ cplx dif_bin(const double2* sl, const double2* tw512, int m) {
+    const int p = dif_pos<N>(m);
+    const int f = (m >> (3 * (Log8<N>::value - 1))) & 7;
+    cplx acc = {0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const cplx v = lds_c(sl, p + r);
+        const double2 w = tw512[((r * f) & 7) << 6];
+        acc.re = fma(v.re, w.x, fma(-v.im, w.y, acc.re));
+        if (WANT_IM) acc.im = fma(v.re, w.y, fma(v.im, w.x, acc.im));
+    }
+    return acc;
 }
 
 }  // namespace hb

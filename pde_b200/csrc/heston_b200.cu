@@ -134,6 +134,8 @@ int set_smem(K kernel, size_t bytes) {
 
 int gmax_for(int N) { return (N == 4096 || N == 512) ? 3 : 1; }
 size_t fft_smem_bytes(int N, int g) { return (size_t)g * N * 16 + (size_t)(N / 8) * 16; }
+// fused kernel: slices + W_N table + W_512 table (fft_smem.cuh, dif_pass)
+size_t job_smem_bytes(int N, int g) { return fft_smem_bytes(N, g) + 512 * 16; }
 
 // Launch the pricing pipeline for P parameter sets (device SoA) and the requested output.
 int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, double* d_out, double* d_out2,
@@ -175,7 +177,7 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
             if (rc) return rc;
             scratch = (double*)pl->scratch.dev;
         }
-        const size_t smem = fft_smem_bytes(pl->Nsub, gmax);
+        const size_t smem = job_smem_bytes(pl->Nsub, gmax);
         if (pl->Nsub == 4096) {
             if (pl->R == 1)
                 fft_job_kernel<4096, kNT4096, false><<<grid, kNT4096, smem, st>>>(
@@ -311,9 +313,9 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     std::memcpy(pl->bd.lb, lb, sizeof lb);
     std::memcpy(pl->bd.ub, ub, sizeof ub);
     if (mode == HB_MODE_FFT) {
-        int rc = (n_grid > 4096)    ? set_smem(fft_job_kernel<4096, kNT4096, true>, fft_smem_bytes(4096, gmax_for(4096)))
-                 : (n_grid == 4096) ? set_smem(fft_job_kernel<4096, kNT4096, false>, fft_smem_bytes(4096, gmax_for(4096)))
-                                    : set_smem(fft_job_kernel<512, kNT512, false>, fft_smem_bytes(512, gmax_for(512)));
+        int rc = (n_grid > 4096)    ? set_smem(fft_job_kernel<4096, kNT4096, true>, job_smem_bytes(4096, gmax_for(4096)))
+                 : (n_grid == 4096) ? set_smem(fft_job_kernel<4096, kNT4096, false>, job_smem_bytes(4096, gmax_for(4096)))
+                                    : set_smem(fft_job_kernel<512, kNT512, false>, job_smem_bytes(512, gmax_for(512)));
         if (rc) {
             delete pl;
             return rc;
@@ -391,16 +393,16 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
         by_mat[m].push_back(i);
     }
     std::vector<double> mat_disc(M), mat_fwd(M);
-    std::vector<int> mat_off(M + 1, 0), opt_orig, opt_bin, need_off(M + 1, 0), need_q;
+    std::vector<int> mat_off(M + 1, 0), opt_orig, opt_bin;
+    std::vector<unsigned> need_mask(M, 0u);
     std::vector<double> opt_frac, opt_s0, opt_s1, opt_lnk, opt_kdisc;
     std::vector<uint8_t> opt_call;
-    const int Nsub = pl->Nsub, NB = std::max(Nsub / 8, 1);
+    const int Nsub = pl->Nsub;
     for (int m = 0; m < M; ++m) {
         const double T = mats[m];
         const double disc = std::exp(-rate * T);  // heston.cpp:106
         mat_disc[m] = disc;
         mat_fwd[m] = spot * std::exp(-dividend * T);  // heston.cpp:148
-        std::vector<int> qs;
         for (int i : by_mat[m]) {
             const double K = strike[i], k = std::log(K);
             opt_orig.push_back(i);
@@ -422,8 +424,11 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                     opt_frac.push_back((k - km) / lambda);
                     opt_s0.push_back(std::exp(-alpha * km) / kPi);
                     opt_s1.push_back(std::exp(-alpha * km1) / kPi);
-                    qs.push_back((mm % Nsub) % NB);  // last-pass butterfly of the on-chip transform
-                    qs.push_back(((mm + 1) % Nsub) % NB);
+                    // digit of the on-chip transform's output index that the S = 8 pass resolves
+                    for (int h = 0; h < 2; ++h) {
+                        const int ms = (mm + h) % Nsub;
+                        need_mask[m] |= 1u << (Nsub == 4096 ? dif_mask_digit<4096>(ms) : dif_mask_digit<512>(ms));
+                    }
                 }
             } else {
                 opt_bin.push_back(0);
@@ -432,10 +437,6 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                 opt_s1.push_back(0.0);
             }
         }
-        std::sort(qs.begin(), qs.end());
-        qs.erase(std::unique(qs.begin(), qs.end()), qs.end());
-        need_q.insert(need_q.end(), qs.begin(), qs.end());
-        need_off[m + 1] = (int)need_q.size();
         mat_off[m + 1] = (int)opt_orig.size();
     }
     std::vector<double> mkt(n_opt, nan);
@@ -445,7 +446,7 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     const size_t o_T = bb.add(mats), o_disc = bb.add(mat_disc), o_fwd = bb.add(mat_fwd), o_moff = bb.add(mat_off),
                  o_orig = bb.add(opt_orig), o_bin = bb.add(opt_bin), o_frac = bb.add(opt_frac), o_s0 = bb.add(opt_s0),
                  o_s1 = bb.add(opt_s1), o_lnk = bb.add(opt_lnk), o_kd = bb.add(opt_kdisc), o_call = bb.add(opt_call),
-                 o_noff = bb.add(need_off), o_nq = bb.add(need_q), o_io = bb.add(intr_orig), o_iv = bb.add(intr_val),
+                 o_nm = bb.add(need_mask), o_io = bb.add(intr_orig), o_iv = bb.add(intr_val),
                  o_mkt = bb.add(mkt);
     const size_t o_K = bb.add(std::vector<double>(strike, strike + n_opt)),
                  o_Tm = bb.add(std::vector<double>(maturity, maturity + n_opt)),
@@ -477,8 +478,7 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     S.opt_lnk = (const double*)(base + o_lnk);
     S.opt_kdisc = (const double*)(base + o_kd);
     S.opt_call = (const uint8_t*)(base + o_call);
-    S.need_off = (const int*)(base + o_noff);
-    S.need_q = (const int*)(base + o_nq);
+    S.need_mask = (const unsigned*)(base + o_nm);
     S.intr_orig = (const int*)(base + o_io);
     S.intr_val = (const double*)(base + o_iv);
     S.mkt_orig = (const double*)(base + o_mkt);

@@ -50,8 +50,7 @@ struct SurfaceDev {
     const double* opt_lnk;   // ln K
     const double* opt_kdisc; // K exp(-r T) (put parity, heston.cpp:148)
     const uint8_t* opt_call;
-    const int* need_off;     // [n_mat+1] pruned last-pass butterflies per maturity
-    const int* need_q;
+    const unsigned* need_mask;  // [n_mat] FFT: digits m_{L-2} of the quoted bins (outputs kept by the S = 8 pass)
     const int* intr_orig;    // options not priced through a slice (T == 0 or invalid)
     const double* intr_val;  // intrinsic value or NaN
     const double* mkt_orig;  // [n_opt] market prices in caller order (may be null for W_PRICE)
@@ -80,6 +79,7 @@ struct SubSlice {
 struct Group {
     ClassConst cc;
     int count;
+    unsigned fmask[kMaxGroup];  // need_mask of each slice's maturity
     SubSlice s[kMaxGroup];
 };
 
@@ -164,6 +164,7 @@ __device__ __forceinline__ void fill_group(Group& grp, const JobState& js, const
         s.lsm = S.ln_spot + (S.rate - S.dividend) * s.T;
         s.disc = S.mat_disc[mat];
         s.fwd = S.mat_fwd[mat];
+        grp.fmask[g] = S.need_mask ? S.need_mask[mat] : 0xffu;
     }
 }
 
@@ -316,6 +317,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* slices = reinterpret_cast<double2*>(smem_raw);
     double2* tw = slices + (size_t)gmax * N;
+    double2* tw512 = tw + N / 8;
     __shared__ Group grp;
     __shared__ JobState js;
     __shared__ double red[(NT / 32) * 23];
@@ -332,6 +334,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     const long long n_jobs = split ? (long long)P * groups_per_set : (long long)P;
 
     fill_twiddles<N>(tw, tid, NT);
+    fill_tw512(tw512, tid, NT);
 
     constexpr int PTS = DECIM ? 1 : (N + NT - 1) / NT;  // grid points owned by one thread
     StageA ac[PTS];
@@ -469,44 +472,51 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     }
                 }
             }
+            // ---- K2: in-place decimation-in-frequency passes in shared memory (fft_smem.cuh) ----
+            // Pass 1: butterfly `tid` reads the points tid + r N/8 this thread has just written -> no barrier.
+            if (N / 8 != NT) __syncthreads();
+            dif_pass<N, NT, N / 8, false>(slices, count, tw, tw512, grp.fmask, tid);
             __syncthreads();
-            // ---- K2: Stockham FFT in shared memory, last pass pruned to the quoted bins ----
-            for (int Ns = 1; Ns < N / 8; Ns *= 8) fft_pass<N, NT>(slices, count, gmax, tw, Ns, tid);
-            __syncthreads();
-            for (int g = 0; g < count; ++g) {
-                const int mat = grp.s[g].mat;
-                const int q0 = S.need_off[mat];
-                fft_last_pass_pruned<N, NT>(slices + (size_t)g * N, tw, S.need_q + q0, S.need_off[mat + 1] - q0, tid);
+            if (N >= 4096) {
+                dif_pass<N, NT, (N >= 4096 ? N / 64 : 8), false>(slices, count, tw, tw512, grp.fmask, tid);
+                __syncthreads();
             }
+            dif_pass<N, NT, 8, true>(slices, count, tw, tw512, grp.fmask, tid);  // only the digits the strikes need
             __syncthreads();
-            // ---- K3: log-strike interpolation (accumulated over phases), clamp, parity -> price rows ----
+            // ---- K3: last butterfly output at the two bracketing bins (two threads per option), log-strike
+            // interpolation (accumulated over phases), clamp, parity -> price rows ----
             for (int g = 0; g < count; ++g) {
                 const SubSlice& s = grp.s[g];
                 const double2* sl = slices + (size_t)g * N;
-                const int o1 = S.mat_off[s.mat + 1];
-                for (int o = S.mat_off[s.mat] + tid; o < o1; o += NT) {
-                    const int bin = S.opt_bin[o];
-                    double* dst = rows + (size_t)s.variant * n + S.opt_orig[o];
-                    double price = __longlong_as_double(0x7ff8000000000000LL);
+                const int o0 = S.mat_off[s.mat], o1 = S.mat_off[s.mat + 1];
+                for (int ob = o0; ob < o1; ob += NT / 2) {  // block-uniform trip count (shuffles inside)
+                    const int o = ob + (tid >> 1), half = tid & 1;
+                    const bool live = o < o1;
+                    const int bin = live ? S.opt_bin[o] : -1;
+                    double x = 0.0;
                     if (bin >= 0) {
-                        const double2 y0 = sl[swz(bin & (N - 1))];
-                        const double2 y1 = sl[swz((bin + 1) & (N - 1))];
-                        double x0 = y0.x, x1 = y1.x;
+                        const int m = bin + half;
+                        const cplx y = dif_bin<N, DECIM>(sl, tw512, m & (N - 1));
+                        x = y.re;
                         if (DECIM) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
                             double sn, cs;
-                            sincospi(-2.0 * (double)(((long long)ph * bin) % gc.n_full) / (double)gc.n_full, &sn, &cs);
-                            x0 = y0.x * cs - y0.y * sn;
-                            sincospi(-2.0 * (double)(((long long)ph * (bin + 1)) % gc.n_full) / (double)gc.n_full, &sn,
-                                     &cs);
-                            x1 = y1.x * cs - y1.y * sn;
+                            sincospi(-2.0 * (double)(((long long)ph * m) % gc.n_full) / (double)gc.n_full, &sn, &cs);
+                            x = y.re * cs - y.im * sn;
                         }
-                        const double c0 = S.opt_s0[o] * x0;
-                        const double c1 = S.opt_s1[o] * x1;
-                        double call = s.disc * (c0 + (c1 - c0) * S.opt_frac[o]);
-                        if (ph > 0) call += *dst;
-                        price = (ph == R - 1) ? finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]) : call;
                     }
-                    *dst = price;
+                    const double x1 = __shfl_xor_sync(0xffffffffu, x, 1);
+                    if (live && half == 0) {
+                        double* dst = rows + (size_t)s.variant * n + S.opt_orig[o];
+                        double price = __longlong_as_double(0x7ff8000000000000LL);
+                        if (bin >= 0) {
+                            const double c0 = S.opt_s0[o] * x;
+                            const double c1 = S.opt_s1[o] * x1;
+                            double call = s.disc * (c0 + (c1 - c0) * S.opt_frac[o]);
+                            if (ph > 0) call += *dst;
+                            price = (ph == R - 1) ? finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]) : call;
+                        }
+                        *dst = price;
+                    }
                 }
             }
             __syncthreads();  // slices and grp are free again

@@ -75,10 +75,12 @@ constexpr int kMaxGroup = 3;
 struct SubSlice {
     double T, kts, v0s, lsm, disc, fwd;
     int mat, variant;
+    int o0, o1;  // options of this maturity: sorted indices [o0, o1)
 };
 struct Group {
     ClassConst cc;
     int count;
+    int max_opt;                // max over slices of o1 - o0
     unsigned fmask[kMaxGroup];  // need_mask of each slice's maturity
     SubSlice s[kMaxGroup];
 };
@@ -151,6 +153,7 @@ __device__ __forceinline__ void fill_group(Group& grp, const JobState& js, const
     grp.cc.rs = xc[3] * xc[2];
     const int cnt = min(gmax, n_total - t0);
     grp.count = cnt;
+    int max_opt = 0;
     for (int g = 0; g < cnt; ++g) {
         int variant, mat;
         sub_slice_at(cls, V, t0 + g, variant, mat);
@@ -164,8 +167,12 @@ __device__ __forceinline__ void fill_group(Group& grp, const JobState& js, const
         s.lsm = S.ln_spot + (S.rate - S.dividend) * s.T;
         s.disc = S.mat_disc[mat];
         s.fwd = S.mat_fwd[mat];
+        s.o0 = S.mat_off[mat];
+        s.o1 = S.mat_off[mat + 1];
+        max_opt = max(max_opt, s.o1 - s.o0);
         grp.fmask[g] = S.need_mask ? S.need_mask[mat] : 0xffu;
     }
+    grp.max_opt = max_opt;
 }
 
 // ---- block reductions ---------------------------------------------------------------------
@@ -318,7 +325,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     double2* slices = reinterpret_cast<double2*>(smem_raw);
     double2* tw = slices + (size_t)gmax * N;
     double2* tw512 = tw + N / 8;
-    __shared__ Group grp;
+    __shared__ Group grps[2];  // descriptor of the running group and, prefetched during its K1, of the next one
     __shared__ JobState js;
     __shared__ double red[(NT / 32) * 23];
     const int tid = threadIdx.x;
@@ -337,16 +344,17 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     fill_tw512(tw512, tid, NT);
 
     constexpr int PTS = DECIM ? 1 : (N + NT - 1) / NT;  // grid points owned by one thread
+    static_assert(PTS <= 8, "one byte of dead-point flags per maturity");
     StageA ac[PTS];
     cplx tabc[PTS];
-    // dead[k] bit m: the base set's phi at this thread's k-th point and maturity m has underflowed with
-    // a wide margin (see K1).  Only available when one CTA prices all classes of a set.
-    constexpr int kDeadWords = 2;  // 128 maturities
-    unsigned long long dead[PTS][kDeadWords];
+    // deadm: one byte per maturity m, bit k: the base set's phi at this thread's k-th point and maturity m
+    // has underflowed with a wide margin (see K1).  Only available when one CTA prices all classes of a set.
+    constexpr int kDeadWords = 8;  // 64 maturities
+    unsigned long long deadm[kDeadWords];
 #ifndef HB_TAIL
 #define HB_TAIL 1
 #endif
-    const bool track_tail = HB_TAIL && !DECIM && !split && V > 1 && M <= 64 * kDeadWords;
+    const bool track_tail = HB_TAIL && !DECIM && !split && V > 1 && M <= 8 * kDeadWords;
 
     // Jobs differ in cost (decayed tails take the short path of stage F), so after its first,
     // statically assigned job a CTA pulls the next one from a global counter.
@@ -358,21 +366,66 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
         __syncthreads();
         return s_job;
     };
+    // group gi of a set -> (class, first sub-slice)
+    auto group_at = [&](int gi, int& cls, int& n_total, int& t0) {
+        const int ci = (gi < g0) ? 0 : 1 + (gi - g0) / g1;
+        cls = (ci == 0) ? 0 : (ci == 1 ? 1 : (ci == 2 ? 3 : 4));  // base | kappa' | sigma' | rho'
+        n_total = (V > 1 && cls == 0) ? 3 * M : M;
+        t0 = ((gi < g0) ? gi : (gi - g0) % g1) * gmax;
+    };
+
+    // K3 works on all slices of a group at once: TPG threads per slice, two threads per option (one per
+    // bracketing bin).  The option's constants are loaded one step ahead (before the last FFT pass /
+    // before the previous batch is finished) so their latency is off the critical path.
+    constexpr int TPG = (NT / kMaxGroup) & ~1;
+    struct K3Opt {
+        int o, bin, orig, call;
+        double s0, s1, frac, kdisc;
+    };
+    const int k3_g = tid / TPG, k3_lt = tid - k3_g * TPG, k3_half = k3_lt & 1;
+    auto k3_load = [&](const Group& grp, int base) -> K3Opt {
+        K3Opt q;
+        q.o = -1;
+        q.bin = -1;
+        q.orig = q.call = 0;
+        q.s0 = q.s1 = q.frac = q.kdisc = 0.0;
+        if (k3_g < grp.count) {
+            const int o = grp.s[k3_g].o0 + base + (k3_lt >> 1);
+            if (o < grp.s[k3_g].o1) {
+                q.o = o;
+                q.bin = S.opt_bin[o];
+                if (k3_half == 0) {
+                    q.orig = S.opt_orig[o];
+                    q.call = S.opt_call[o];
+                    q.s0 = S.opt_s0[o];
+                    q.s1 = S.opt_s1[o];
+                    q.frac = S.opt_frac[o];
+                    q.kdisc = S.opt_kdisc[o];
+                }
+            }
+        }
+        return q;
+    };
 
     for (long long job = blockIdx.x; job < n_jobs; job = next_job(job)) {
         const int p = split ? (int)(job / groups_per_set) : (int)job;
         const int gi_begin = split ? (int)(job % groups_per_set) : 0;
         const int gi_end = split ? gi_begin + 1 : groups_per_set;
-        int cached_cls = -1;  // class whose stage A sits in ac[]
+        int cached_cls = -1;    // class whose stage A sits in ac[]
         int job_has_dead = -1;  // -1: not known yet (class 0 still running)
         if (track_tail) {
 #pragma unroll
-            for (int k = 0; k < PTS; ++k)
-#pragma unroll
-                for (int w = 0; w < kDeadWords; ++w) dead[k][w] = 0ull;
+            for (int w = 0; w < kDeadWords; ++w) deadm[w] = 0ull;
         }
         __syncthreads();  // previous job's finalize has consumed rows/js
-        if (tid == 0) job_setup(js, params, ld, p, bd, V);
+        if (tid == 0) {
+            job_setup(js, params, ld, p, bd, V);
+            if (js.valid) {
+                int cls, n_total, t0;
+                group_at(gi_begin, cls, n_total, t0);
+                fill_group(grps[gi_begin & 1], js, S, cls, V, t0, n_total, gmax);
+            }
+        }
         __syncthreads();
         if (!js.valid) {
             if (!split) invalid_job<NT>(what, S, p, out, out2, tid);
@@ -386,19 +439,23 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 for (int i = tid; i < S.n_intr; i += NT) rows[(size_t)v * n + S.intr_orig[i]] = S.intr_val[i];
         }
         for (int gi = gi_begin; gi < gi_end; ++gi) {
-            const int ci = (gi < g0) ? 0 : 1 + (gi - g0) / g1;
-            const int cls = (ci == 0) ? 0 : (ci == 1 ? 1 : (ci == 2 ? 3 : 4));  // base | kappa' | sigma' | rho'
-            const int n_total = (V > 1 && cls == 0) ? 3 * M : M;
-            const int t0 = ((gi < g0) ? gi : (gi - g0) % g1) * gmax;
-            if (tid == 0) fill_group(grp, js, S, cls, V, t0, n_total, gmax);
+            int cls, n_total, t0;
+            group_at(gi, cls, n_total, t0);
+            const Group& grp = grps[gi & 1];  // filled before the previous barrier
+            // The next group's descriptor is built by one thread while K1 runs (its global loads would
+            // otherwise sit between two barriers with the whole CTA waiting); the other buffer was last
+            // read before the barrier that ended group gi - 1.
+            if (tid == NT - 1 && gi + 1 < gi_end) {
+                int cls2, n2, t2;
+                group_at(gi + 1, cls2, n2, t2);
+                fill_group(grps[(gi + 1) & 1], js, S, cls2, V, t2, n2, gmax);
+            }
             if (track_tail && cls != 0 && job_has_dead < 0) {
                 // class 0 is done: does any thread of the CTA hold a decayed point?  (block-uniform)
                 unsigned long long any = 0ull;
 #pragma unroll
-                for (int k = 0; k < PTS; ++k) any |= dead[k][0] | dead[k][1];
+                for (int w = 0; w < kDeadWords; ++w) any |= deadm[w];
                 job_has_dead = __syncthreads_or(any != 0ull);
-            } else {
-                __syncthreads();
             }
             const int count = grp.count;
             const int R = DECIM ? gc.R : 1;  // DECIM = false: the plain single-transform kernel (N == Nsub)
@@ -427,16 +484,19 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 // the group is dead skip stage B and F.  skip bit k <-> this thread's k-th point.
                 unsigned skip = 0u;
                 if (track_tail && cls != 0 && job_has_dead) {
-                    const int m0 = grp.s[0].mat;  // a perturbed class walks maturities in order: slice g = m0 + g
-                    const unsigned long long want = (1ull << count) - 1ull;
+                    skip = 0xffu;
+                    for (int g = 0; g < count; ++g) {
+                        const int mat = grp.s[g].mat;
+                        unsigned long long word = 0ull;
 #pragma unroll
-                    for (int k = 0; k < PTS; ++k) {
-                        const unsigned long long lo = dead[k][0], hi = dead[k][1];
-                        const unsigned long long bits =
-                            (m0 < 64) ? ((lo >> m0) | (m0 ? (hi << (64 - m0)) : 0ull)) : (hi >> (m0 - 64));
-                        skip |= ((bits & want) == want ? 1u : 0u) << k;
+                        for (int w = 0; w < kDeadWords; ++w) word = (w == (mat >> 3)) ? deadm[w] : word;
+                        skip &= (unsigned)(word >> ((mat & 7) * 8));
                     }
+                    skip &= 0xffu;
                 }
+                // class 0 records the base slice's decayed points (slice 0 of a class-0 group is the base set)
+                const bool record = track_tail && cls == 0 && grp.s[0].variant == 0;
+                unsigned dmask = 0u;
 #pragma unroll 1
                 for (int k = 0, j0 = tid; j0 < N; ++k, j0 += NT) {
                     const int j = ph + R * j0;  // index on the full N-point grid
@@ -467,9 +527,15 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         const SliceConst sc = {s.kts, s.v0s, s.lsm};
                         double er;
                         const cplx phi = stage_f(b, sc, v, gc.ui, &er);
-                        if (track_tail && s.variant == 0 && er < -800.0) dead[k][s.mat >> 6] |= 1ull << (s.mat & 63);
+                        if (g == 0) dmask |= (er < -800.0 ? 1u : 0u) << k;
                         sts_c(slices + (size_t)g * N, j0, cmul(phi, tab));
                     }
+                }
+                if (record) {
+                    const int mat = grp.s[0].mat;
+                    const unsigned long long bits = (unsigned long long)dmask << ((mat & 7) * 8);
+#pragma unroll
+                    for (int w = 0; w < kDeadWords; ++w) deadm[w] |= (w == (mat >> 3)) ? bits : 0ull;
                 }
             }
             // ---- K2: in-place decimation-in-frequency passes in shared memory (fft_smem.cuh) ----
@@ -481,21 +547,22 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 dif_pass<N, NT, (N >= 4096 ? N / 64 : 8), false>(slices, count, tw, tw512, grp.fmask, tid);
                 __syncthreads();
             }
+            K3Opt cur = k3_load(grp, 0);
             dif_pass<N, NT, 8, true>(slices, count, tw, tw512, grp.fmask, tid);  // only the digits the strikes need
             __syncthreads();
-            // ---- K3: last butterfly output at the two bracketing bins (two threads per option), log-strike
-            // interpolation (accumulated over phases), clamp, parity -> price rows ----
-            for (int g = 0; g < count; ++g) {
-                const SubSlice& s = grp.s[g];
-                const double2* sl = slices + (size_t)g * N;
-                const int o0 = S.mat_off[s.mat], o1 = S.mat_off[s.mat + 1];
-                for (int ob = o0; ob < o1; ob += NT / 2) {  // block-uniform trip count (shuffles inside)
-                    const int o = ob + (tid >> 1), half = tid & 1;
-                    const bool live = o < o1;
-                    const int bin = live ? S.opt_bin[o] : -1;
+            // ---- K3: last butterfly output at the two bracketing bins, log-strike interpolation
+            // (accumulated over phases), clamp, parity -> price rows ----
+            {
+                const int max_opt = grp.max_opt;
+                const int gg = (k3_g < count) ? k3_g : 0;
+                const SubSlice& s = grp.s[gg];
+                const double2* sl = slices + (size_t)gg * N;
+                for (int base = 0; base < max_opt; base += TPG / 2) {  // block-uniform trip count (shuffles inside)
+                    K3Opt nxt = cur;
+                    if (base + TPG / 2 < max_opt) nxt = k3_load(grp, base + TPG / 2);
                     double x = 0.0;
-                    if (bin >= 0) {
-                        const int m = bin + half;
+                    if (cur.bin >= 0) {
+                        const int m = cur.bin + k3_half;
                         const cplx y = dif_bin<N, DECIM>(sl, tw512, m & (N - 1));
                         x = y.re;
                         if (DECIM) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
@@ -505,21 +572,22 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         }
                     }
                     const double x1 = __shfl_xor_sync(0xffffffffu, x, 1);
-                    if (live && half == 0) {
-                        double* dst = rows + (size_t)s.variant * n + S.opt_orig[o];
+                    if (cur.o >= 0 && k3_half == 0) {
+                        double* dst = rows + (size_t)s.variant * n + cur.orig;
                         double price = __longlong_as_double(0x7ff8000000000000LL);
-                        if (bin >= 0) {
-                            const double c0 = S.opt_s0[o] * x;
-                            const double c1 = S.opt_s1[o] * x1;
-                            double call = s.disc * (c0 + (c1 - c0) * S.opt_frac[o]);
+                        if (cur.bin >= 0) {
+                            const double c0 = cur.s0 * x;
+                            const double c1 = cur.s1 * x1;
+                            double call = s.disc * (c0 + (c1 - c0) * cur.frac);
                             if (ph > 0) call += *dst;
-                            price = (ph == R - 1) ? finish_price(call, S.opt_call[o] != 0, s.fwd, S.opt_kdisc[o]) : call;
+                            price = (ph == R - 1) ? finish_price(call, cur.call != 0, s.fwd, cur.kdisc) : call;
                         }
                         *dst = price;
                     }
+                    cur = nxt;
                 }
             }
-            __syncthreads();  // slices and grp are free again
+            __syncthreads();  // slices are free again; the prefetched descriptor of group gi + 1 is visible
             }
         }
         if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);

@@ -211,12 +211,30 @@ __device__ __forceinline__ void dif_pass(double2* base, int count, const double2
     constexpr int PER = (NB + NT - 1) / NT;
     static_assert(NB % NT == 0 || NB < NT, "butterflies must tile over the block");
     constexpr bool RUNNING = (8 * S == N) && (N > 512);
+    constexpr int STEP = (8 * S <= 512) ? 512 / (8 * S) : 1;  // W_{8S}^k = W_512^{k STEP}
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int b = tid + u * NT;
         if (b < NB) {
             const int t = b & (S - 1);
             const int p0 = ((b - t) << 3) + t;
+            // twiddles of this butterfly, shared by all slices of the group (a full pass needs all seven;
+            // the masked pass looks its one or two up per slice)
+            cplx wf[8];
+            if (!MASKED) {
+                if (RUNNING) {
+                    const double2 w = tw[t];
+                    wf[1] = {w.x, w.y};
+#pragma unroll
+                    for (int f = 2; f < 8; ++f) wf[f] = cmul(wf[f - 1], wf[1]);
+                } else {
+#pragma unroll
+                    for (int f = 1; f < 8; ++f) {
+                        const double2 w = tw512[(t * f * STEP) & 511];
+                        wf[f] = {w.x, w.y};
+                    }
+                }
+            }
 #pragma unroll 1
             for (int g = 0; g < count; ++g) {
                 double2* sl = base + (size_t)g * N;
@@ -225,24 +243,13 @@ __device__ __forceinline__ void dif_pass(double2* base, int count, const double2
 #pragma unroll
                 for (int r = 0; r < 8; ++r) v[r] = lds_c(sl, p0 + r * S);
                 dft8(v);  // X_f in v[bitrev3(f)]
-                if (RUNNING) {
-                    const double2 w = tw[t];
-                    const cplx w1 = {w.x, w.y};
-                    cplx wp = w1;
-                    v[bitrev3(1)] = cmul(v[bitrev3(1)], wp);
 #pragma unroll
-                    for (int f = 2; f < 8; ++f) {
-                        wp = cmul(wp, w1);
-                        v[bitrev3(f)] = cmul(v[bitrev3(f)], wp);
-                    }
-                } else {
-                    constexpr int STEP = 512 / (8 * S);
-#pragma unroll
-                    for (int f = 1; f < 8; ++f) {
-                        if (!MASKED || ((keep >> f) & 1u)) {
-                            const double2 w = tw512[(t * f * STEP) & 511];
-                            v[bitrev3(f)] = cmul(v[bitrev3(f)], {w.x, w.y});
-                        }
+                for (int f = 1; f < 8; ++f) {
+                    if (!MASKED) {
+                        v[bitrev3(f)] = cmul(v[bitrev3(f)], wf[f]);
+                    } else if ((keep >> f) & 1u) {
+                        const double2 w = tw512[(t * f * STEP) & 511];
+                        v[bitrev3(f)] = cmul(v[bitrev3(f)], {w.x, w.y});
                     }
                 }
 #pragma unroll

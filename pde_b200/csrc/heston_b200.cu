@@ -192,8 +192,14 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
         g_launches++;
         HB_CUDA(cudaGetLastError());
         if (split && what != W_PRICE) {
-            finalize_rows_kernel<256><<<std::min(P, 4 * max_ctas), 256, 0, st>>>(S, pl->bd, d_params, ld, P, what,
-                                                                                  scratch, d_out, d_out2);
+            // same block size as the job kernel: the in-kernel finalize and this one then reduce in the
+            // same order, so split and persistent launches agree bit for bit
+            if (pl->Nsub == 4096)
+                finalize_rows_kernel<kNT4096><<<std::min(P, 4 * max_ctas), kNT4096, 0, st>>>(
+                    S, pl->bd, d_params, ld, P, what, scratch, d_out, d_out2);
+            else
+                finalize_rows_kernel<kNT512><<<std::min(P, 4 * max_ctas), kNT512, 0, st>>>(
+                    S, pl->bd, d_params, ld, P, what, scratch, d_out, d_out2);
             g_launches++;
             HB_CUDA(cudaGetLastError());
         }

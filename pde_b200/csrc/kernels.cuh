@@ -349,7 +349,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     cplx tabc[PTS];
     // deadm: one byte per maturity m, bit k: the base set's phi at this thread's k-th point and maturity m
     // has underflowed with a wide margin (see K1).  Only available when one CTA prices all classes of a set.
-    constexpr int kDeadWords = 8;  // 64 maturities
+    // Indexed dynamically, once per group: lives in local memory, not in registers.
+    constexpr int kDeadWords = 16;  // 128 maturities
     unsigned long long deadm[kDeadWords];
 #ifndef HB_TAIL
 #define HB_TAIL 1
@@ -487,15 +488,14 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     skip = 0xffu;
                     for (int g = 0; g < count; ++g) {
                         const int mat = grp.s[g].mat;
-                        unsigned long long word = 0ull;
-#pragma unroll
-                        for (int w = 0; w < kDeadWords; ++w) word = (w == (mat >> 3)) ? deadm[w] : word;
-                        skip &= (unsigned)(word >> ((mat & 7) * 8));
+                        skip &= (unsigned)(deadm[mat >> 3] >> ((mat & 7) * 8));
                     }
                     skip &= 0xffu;
                 }
                 // class 0 records the base slice's decayed points (slice 0 of a class-0 group is the base set)
                 const bool record = track_tail && cls == 0 && grp.s[0].variant == 0;
+                // a class-0 group of the 6-variant mode is {base, theta', v0'} of ONE maturity: stage B is shared
+                const bool share_b = V > 1 && cls == 0 && gmax == 3;
                 unsigned dmask = 0u;
 #pragma unroll 1
                 for (int k = 0, j0 = tid; j0 < N; ++k, j0 += NT) {
@@ -516,14 +516,10 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         tab = tabc[k];
                     }
                     StageB b = {};
-                    double Tprev = -1.0;
 #pragma unroll 1
                     for (int g = 0; g < count; ++g) {
                         const SubSlice& s = grp.s[g];
-                        if (s.T != Tprev) {  // slices of one maturity (base, theta', v0') share stage B
-                            b = stage_b(a, s.T);
-                            Tprev = s.T;
-                        }
+                        if (g == 0 || !share_b) b = stage_b(a, s.T);
                         const SliceConst sc = {s.kts, s.v0s, s.lsm};
                         double er;
                         const cplx phi = stage_f(b, sc, v, gc.ui, &er);
@@ -533,9 +529,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 }
                 if (record) {
                     const int mat = grp.s[0].mat;
-                    const unsigned long long bits = (unsigned long long)dmask << ((mat & 7) * 8);
-#pragma unroll
-                    for (int w = 0; w < kDeadWords; ++w) deadm[w] |= (w == (mat >> 3)) ? bits : 0ull;
+                    deadm[mat >> 3] |= (unsigned long long)dmask << ((mat & 7) * 8);
                 }
             }
             // ---- K2: in-place decimation-in-frequency passes in shared memory (fft_smem.cuh) ----

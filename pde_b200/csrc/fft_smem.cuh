@@ -194,10 +194,16 @@ struct Log8<1> {
     static constexpr int value = 0;
 };
 
+// Twiddle tables behind the W_N one: W_512^k (512 entries), W_64^k (64), w8^k (8), each compact so that
+// consecutive lanes read consecutive 16-byte slots (a strided walk through the 512-entry table would put
+// all lanes of the S = 8 pass on one bank group).
+constexpr int kTwSmall = 512 + 64 + 8;
 __device__ __forceinline__ void fill_tw512(double2* t512, int tid, int nthreads) {
-    for (int k = tid; k < 512; k += nthreads) {
+    for (int k = tid; k < kTwSmall; k += nthreads) {
+        const int n = (k < 512) ? 512 : (k < 576 ? 64 : 8);
+        const int kk = (k < 512) ? k : (k < 576 ? k - 512 : k - 576);
         double sn, cs;
-        sincospi(-(double)k / 256.0, &sn, &cs);
+        sincospi(-2.0 * (double)kk / (double)n, &sn, &cs);
         t512[k] = make_double2(cs, sn);
     }
 }
@@ -210,8 +216,10 @@ __device__ __forceinline__ void dif_pass(double2* base, int count, const double2
     constexpr int NB = N / 8;
     constexpr int PER = (NB + NT - 1) / NT;
     static_assert(NB % NT == 0 || NB < NT, "butterflies must tile over the block");
+    static_assert(8 * S == N || 8 * S == 512 || 8 * S == 64, "twiddle table for this stride");
     constexpr bool RUNNING = (8 * S == N) && (N > 512);
-    constexpr int STEP = (8 * S <= 512) ? 512 / (8 * S) : 1;  // W_{8S}^k = W_512^{k STEP}
+    const double2* tws = (8 * S == 64) ? tw512 + 512 : tw512;  // W_{8S}^k
+    constexpr int TMASK = (8 * S == 64) ? 63 : 511;
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int b = tid + u * NT;
@@ -230,11 +238,13 @@ __device__ __forceinline__ void dif_pass(double2* base, int count, const double2
                 } else {
 #pragma unroll
                     for (int f = 1; f < 8; ++f) {
-                        const double2 w = tw512[(t * f * STEP) & 511];
+                        const double2 w = tws[(t * f) & TMASK];
                         wf[f] = {w.x, w.y};
                     }
                 }
             }
+            // (Issuing the loads of slice g + 1 before slice g is transformed was tried: unrolled or with
+            // a register rotation it costs 0.9-2 KB of spills at 128 registers -- profiles/r01_shape_sweep.txt.)
 #pragma unroll 1
             for (int g = 0; g < count; ++g) {
                 double2* sl = base + (size_t)g * N;
@@ -248,7 +258,7 @@ __device__ __forceinline__ void dif_pass(double2* base, int count, const double2
                     if (!MASKED) {
                         v[bitrev3(f)] = cmul(v[bitrev3(f)], wf[f]);
                     } else if ((keep >> f) & 1u) {
-                        const double2 w = tw512[(t * f * STEP) & 511];
+                        const double2 w = tws[(t * f) & TMASK];
                         v[bitrev3(f)] = cmul(v[bitrev3(f)], {w.x, w.y});
                     }
                 }
@@ -275,7 +285,7 @@ __device__ __forceinline__ int dif_pos(int m) {
 }
 
 // X_m of a slice that went through every pass down to S = 8: the one needed output of its last
-// radix-8 butterfly.  w8^k = W_512^{64 k}.  WANT_IM = false returns Re X_m only (im = 0).
+// radix-8 butterfly (w8^k from the compact table behind W_512 and W_64).  WANT_IM = false returns Re X_m only (im = 0).
 template <int N, bool WANT_IM>
 __device__ __forceinline__ cplx dif_bin(const double2* sl, const double2* tw512, int m) {
     const int p = dif_pos<N>(m);
@@ -284,7 +294,7 @@ __device__ __forceinline__ cplx dif_bin(const double2* sl, const double2* tw512,
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const cplx v = lds_c(sl, p + r);
-        const double2 w = tw512[((r * f) & 7) << 6];
+        const double2 w = tw512[576 + ((r * f) & 7)];
         acc.re = fma(v.re, w.x, fma(-v.im, w.y, acc.re));
         if (WANT_IM) acc.im = fma(v.re, w.y, fma(v.im, w.x, acc.im));
     }

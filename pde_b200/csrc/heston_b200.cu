@@ -134,8 +134,8 @@ int set_smem(K kernel, size_t bytes) {
 
 int gmax_for(int N) { return (N == 4096 || N == 512) ? 3 : 1; }
 size_t fft_smem_bytes(int N, int g) { return (size_t)g * N * 16 + (size_t)(N / 8) * 16; }
-// fused kernel: slices + W_N table + W_512 table (fft_smem.cuh, dif_pass)
-size_t job_smem_bytes(int N, int g) { return fft_smem_bytes(N, g) + 512 * 16; }
+// fused kernel: slices + W_N table + the small W_512 / W_64 / w8 tables (fft_smem.cuh, dif_pass)
+size_t job_smem_bytes(int N, int g) { return fft_smem_bytes(N, g) + (size_t)kTwSmall * 16; }
 
 // Launch the pricing pipeline for P parameter sets (device SoA) and the requested output.
 int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, double* d_out, double* d_out2,

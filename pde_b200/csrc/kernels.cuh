@@ -352,6 +352,9 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     // Indexed dynamically, once per group: lives in local memory, not in registers.
     constexpr int kDeadWords = 16;  // 128 maturities
     unsigned long long deadm[kDeadWords];
+#ifndef HB_F3
+#define HB_F3 1
+#endif
 #ifndef HB_TAIL
 #define HB_TAIL 1
 #endif
@@ -529,6 +532,32 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         tab = tab_n;
                     }
                     StageB b = {};
+                    if (HB_F3 && share_b && count == 3) {
+                        // {base, theta', v0'} of one maturity: one stage B, then the three final cexps in one
+                        // interleaved evaluation (they underflow together: the sets differ by 1.5e-8 relative)
+                        b = stage_b(a, grp.s[0].T);
+                        if (!DECIM) {
+                            a = ac[kn];
+                            tab_n = tabc[kn];
+                        }
+                        double er[3], ei[3];
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) {
+                            const SubSlice& s = grp.s[g];
+                            er[g] = s.kts * b.B.re + s.v0s * b.Dq.re - gc.ui * s.lsm;  // stage_f, heston.cpp:87-91
+                            ei[g] = s.kts * b.B.im + s.v0s * b.Dq.im + v * s.lsm;
+                        }
+                        dmask |= (er[0] < -800.0 ? 1u : 0u) << k;
+                        double pr[3] = {0.0, 0.0, 0.0}, pi[3] = {0.0, 0.0, 0.0};
+                        if (!(er[0] < -746.0 && er[1] < -746.0 && er[2] < -746.0)) cexp_w<3>(er, ei, pr, pi);
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) {
+                            const bool zero = er[g] < -746.0;  // exactly 0 as in stage_f
+                            const cplx phi = {zero ? 0.0 : pr[g], zero ? 0.0 : pi[g]};
+                            sts_c(slices + (size_t)g * N, j0, cmul(phi, tab));
+                        }
+                        continue;
+                    }
 #pragma unroll 1
                     for (int g = 0; g < count; ++g) {
                         const SubSlice& s = grp.s[g];

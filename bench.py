@@ -170,6 +170,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def measured_traffic(P):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the bench step, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json); null when the launch shape differs."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path))
+    return t["dram_bytes_per_launch"] if (t["sets_per_launch"], t["maturities"], t["strikes"]) == (P, N_MAT, N_STRIKE) else None
+
+
 def workload_config(P):
     return {"workload": f"C3: batched calibration objective + finite-difference Jacobian (J^T J, J^T r blocks), "
                         f"{P} parameter sets x {N_MAT} maturities x {N_STRIKE} strikes per GPU, N={N_GRID}, "
@@ -276,7 +286,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": measured_traffic(P),
                          "peak_source": "DFMA probe (hb_measure_fp64_peak) run in this process; "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_slice_W1": FLOPS_PER_SLICE,

@@ -1,31 +1,28 @@
-// fft_smem.cuh -- in-shared-memory Stockham autosort FFT (complex128, forward sign
-// e^{-2 pi i jm/N}) for one or several length-N slices that stay on chip.
+// fft_smem.cuh -- in-shared-memory radix-8 FFTs (complex128, forward sign e^{-2 pi i jm/N}) for
+// one or several length-N slices that stay on chip.  Two factorisations live here:
+//   * fft_pass:  Stockham autosort decimation-in-time passes producing the whole spectrum in natural
+//                order -- used by the unfused fft_batch_kernel (HBM -> smem -> HBM);
+//   * dif_pass / dif_bin:  in-place decimation-in-frequency passes pruned to the bins Carr-Madan
+//                quotes -- used by the fused fft_job_kernel (second half of this file).
 //
 // Layout.  A slice is N complex128 values (16 B each) in shared memory; element i lives
 // at 16-byte slot swz(i) = i ^ ((i >> 3) & 7).  With LDS.128/STS.128 a warp access is
 // served in four 8-lane phases of 128 B; the XOR swizzle makes every phase of every
-// pass (stride-N/8 reads, stride-Ns writes, including the stride-8 writes of the first
-// pass) hit eight distinct 16-byte bank groups, i.e. conflict-free, at the price of two
-// integer ops per access instead of 12.5 % padding (3 x 64 KiB slices + tables must fit
-// the 227 KiB of one sm_100a CTA).
+// pass of both factorisations (strides N/8, N/64, 8, 1) hit eight distinct 16-byte bank
+// groups, i.e. conflict-free, at the price of two integer ops per access instead of
+// 12.5 % padding (3 x 64 KiB slices + tables must fit the 227 KiB of one sm_100a CTA).
 //
-// Algorithm.  Radix-8 decimation-in-time passes, Ns = 1, 8, 64, ...: butterfly b reads
-// x[b + r N/8], multiplies by W_N^{r k}, k = (b mod Ns) N/(8 Ns), does an in-register
-// 8-point DFT and writes y[(b/Ns) 8 Ns + (b mod Ns) + r Ns].  The pass is in place
-// (load -> __syncthreads -> store), so one thread owns exactly one butterfly per slice
-// (N/8 <= block size).  When several slices are transformed together the barrier of
-// slice s doubles as the store/load fence of slices s-1/s+1, so a pass costs one barrier
-// per slice instead of two.  W_N^k for k < N/8 comes from a shared table (N/8 entries,
-// 8 KiB at N = 4096); the powers W^2..W^7 are formed by multiplication (<= 3 products
-// deep, ~1e-16 relative).
-//
-// The last pass can be PRUNED: Carr-Madan needs Re X_m only at the bins bracketing the
-// quoted strikes, so only the listed butterflies (need_q) are evaluated there -- and
-// because the last pass of an autosort FFT reads and writes the same slots
-// (Ns = N/8 => out index = in index) it needs no barrier between load and store.
+// Autosort DIT (fft_pass).  Passes Ns = 1, 8, 64, ...: butterfly b reads x[b + r N/8],
+// multiplies by W_N^{r k}, k = (b mod Ns) N/(8 Ns), does an in-register 8-point DFT and
+// writes y[(b/Ns) 8 Ns + (b mod Ns) + r Ns].  The pass is in place (load -> __syncthreads
+// -> store), so one thread owns exactly one butterfly per slice (N/8 <= block size).
+// When several slices are transformed together the barrier of slice s doubles as the
+// store/load fence of slices s-1/s+1.  W_N^k for k < N/8 comes from a shared table; the
+// powers W^2..W^7 are formed by multiplication (~1e-16 relative).
 //
 // Reference: none -- /root/reference has no FFT.  Spec: SURVEY.md
-// Appendix B step 5; checked against numpy.fft in tests/test_gpu_parity.py.
+// Appendix B step 5; checked against numpy.fft in tests/test_gpu_parity.py (fft_pass) and
+// through price parity with the oracle's plain radix-2 FFT (dif_pass).
 #pragma once
 #include "heston_math.cuh"
 

@@ -2,7 +2,7 @@
 //
 //   fft_job_kernel      K1+K2+K3 fused: one CTA per parameter-set job; characteristic
 //                       function on the damped grid -> slices in shared memory -> in-place
-//                       Stockham FFT -> log-strike interpolation -> prices / loss /
+//                       radix-8 DIF transform pruned to the quoted bins -> log-strike interpolation -> prices / loss /
 //                       finite-difference normal equations.  psi never touches HBM.
 //   refgrid_job_kernel  K1': the reference's own arithmetic (1023-point quadrature,
 //                       heston.cpp:94-151) as CF-once-per-slice + per-strike twiddle sums.

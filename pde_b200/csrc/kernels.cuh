@@ -518,7 +518,9 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     const int kn = (k + 1 < PTS) ? k + 1 : k;
                     if ((skip >> k) & 1u) {
                         for (int g = 0; g < count; ++g) sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
-                        if (!DECIM) {
+                        // fetch stage A only for a point that will be evaluated: back-to-back fetches into
+                        // the same registers would serialise runs of skipped points on the L2 latency
+                        if (!DECIM && !((skip >> kn) & 1u)) {
                             a = ac[kn];
                             tab_n = tabc[kn];
                         }

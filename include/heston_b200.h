@@ -107,6 +107,13 @@ int hb_jacobian(hb_plan* plan, const double* d_params, int ld, int P, double* d_
  * Same Newton iteration, start and clamps as the reference. */
 int hb_implied_vol(hb_plan* plan, const double* d_params, int ld, int P, double* d_iv, void* stream);
 
+/* Finite-difference Greeks of every (parameter set, option), d_greeks[(p * n_opt + i) * 5 + {delta, gamma,
+ * vega, theta, rho}]: replaces a loop of HestonModel::price_option_with_greeks (heston.cpp:168-217) -- the
+ * same nine price evaluations per option (spot +/- 0.1 %, rate +/- 1e-4, maturity - 1/365, v0 +/- 1e-3)
+ * and the same difference formulas; theta is 0 for maturity <= 1/365.  A set whose v0 - 1e-3 is not
+ * positive gets NaN vega (the reference's constructor throws there). */
+int hb_greeks(hb_plan* plan, const double* d_params, int ld, int P, double* d_greeks, void* stream);
+
 /* Characteristic function phi(u_j; T_m) for every parameter set:
  * d_out[((p * n_T + m) * n_u + j) * 2 + {0,1}]; replaces HestonModel::characteristic_function
  * (heston.cpp:74-92).  d_T, d_ur, d_ui are device arrays. */
@@ -126,6 +133,7 @@ int hb_sync(void* stream);
 int hb_price_host(hb_plan* plan, const double* h_params, int P, double* h_prices);
 int hb_objective_host(hb_plan* plan, const double* h_params, int P, double* h_loss);
 int hb_implied_vol_host(hb_plan* plan, const double* h_params, int P, double* h_iv);
+int hb_greeks_host(hb_plan* plan, const double* h_params, int P, double* h_greeks);
 int hb_normal_eq_host(hb_plan* plan, const double* h_params, int P, double* h_out);
 int hb_jacobian_host(hb_plan* plan, const double* h_params, int P, double* h_res, double* h_jac);
 

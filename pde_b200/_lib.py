@@ -38,6 +38,8 @@ SIGNATURES = {
     "hb_jacobian": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "hb_implied_vol": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "hb_implied_vol_host": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "hb_greeks": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "hb_greeks_host": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "hb_cf": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, C.c_double, C.c_double, C.c_double,
                         _vp, _vp]),
     "hb_fft_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

@@ -92,6 +92,12 @@ struct hb_plan {
     Bounds bd{};
     Arena surf, scratch, io_in, io_out, io_out2, ctr;
     int n_sorted = 0;
+    // caller's option list (host copy) and the bumped sibling plans of hb_greeks: S+, S-, r+, r-, T-
+    std::vector<double> h_strike, h_maturity;
+    std::vector<uint8_t> h_call;
+    hb_plan* sib[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool sib_stale = true;
+    Arena gk;
     const double* d_strike = nullptr;    // caller-order copies for the implied-vol epilogue
     const double* d_maturity = nullptr;
     const uint8_t* d_is_call = nullptr;
@@ -253,6 +259,8 @@ int run_host(hb_plan* pl, const double* h_params, int P, int what, double* h_out
     HB_CUDA(cudaMemcpyAsync(pl->io_in.dev, pin, (size_t)5 * P * sizeof(double), cudaMemcpyHostToDevice, st));
     if (what == 4)
         rc = hb_implied_vol(pl, (const double*)pl->io_in.dev, P, P, (double*)pl->io_out.dev, st);
+    else if (what == 5)
+        rc = hb_greeks(pl, (const double*)pl->io_in.dev, P, P, (double*)pl->io_out.dev, st);
     else
         rc = launch_jobs(pl, (const double*)pl->io_in.dev, P, P, what, (double*)pl->io_out.dev,
                          out2_elems ? (double*)pl->io_out2.dev : nullptr, st);
@@ -334,6 +342,11 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
 int hb_plan_destroy(hb_plan* pl) {
     if (!pl) return HB_OK;
     DeviceGuard guard(pl->device);
+    for (hb_plan*& sp : pl->sib) {
+        hb_plan_destroy(sp);
+        sp = nullptr;
+    }
+    pl->gk.release();
     pl->surf.release();
     pl->scratch.release();
     pl->ctr.release();
@@ -492,6 +505,10 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     pl->d_maturity = (const double*)(base + o_Tm);
     pl->d_is_call = (const uint8_t*)(base + o_ic);
     pl->n_sorted = (int)opt_orig.size();
+    pl->h_strike.assign(strike, strike + n_opt);
+    pl->h_maturity.assign(maturity, maturity + n_opt);
+    pl->h_call.assign(is_call, is_call + n_opt);
+    pl->sib_stale = true;
     pl->has_surface = true;
     pl->has_market = market != nullptr;
     return HB_OK;
@@ -521,6 +538,64 @@ int hb_implied_vol(hb_plan* pl, const double* d_params, int ld, int P, double* d
                                                                  pl->S.dividend, d_iv);
     g_launches++;
     HB_CUDA(cudaGetLastError());
+    return HB_OK;
+}
+
+int hb_greeks(hb_plan* pl, const double* d_params, int ld, int P, double* d_greeks, void* stream) {
+    if (!pl) return fail(HB_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (!pl->has_surface) return fail(HB_ERR_STATE, "hb_surface_set has not been called on this plan");
+    if (P < 0 || ld < P) return fail(HB_ERR_INVALID_ARGUMENT, "need 0 <= P <= ld");
+    const int n = pl->S.n_opt;
+    if (P == 0 || n == 0) return HB_OK;
+    if (!d_params || !d_greeks) return fail(HB_ERR_INVALID_ARGUMENT, "NULL device pointer");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+    // bumped surfaces of price_option_with_greeks, heston.cpp:175-200 (theta reprices at T - 1/365 only
+    // where T > 1/365; the other options keep their maturity there and get theta = 0 in the combine)
+    if (pl->sib_stale) {
+        const double S0 = pl->S.spot, r = pl->S.rate, q = pl->S.dividend, es = S0 * kEpsSpotRel;
+        std::vector<double> Tm(pl->h_maturity);
+        for (double& T : Tm)
+            if (T > kEpsTime) T -= kEpsTime;
+        const double spot[5] = {S0 + es, S0 - es, S0, S0, S0};
+        const double rate[5] = {r, r, r + kEpsRate, r - kEpsRate, r};
+        for (int i = 0; i < 5; ++i) {
+            int rc;
+            if (!pl->sib[i] && (rc = hb_plan_create(pl->mode, pl->N, pl->eta, pl->alpha, pl->device, &pl->sib[i]))) return rc;
+            const double* T = (i == 4) ? Tm.data() : pl->h_maturity.data();
+            if ((rc = hb_surface_set(pl->sib[i], n, pl->h_strike.data(), T, pl->h_call.data(), nullptr, spot[i],
+                                     rate[i], q)))
+                return rc;
+        }
+        pl->sib_stale = false;
+    }
+    // chunk over parameter sets so the eight price planes stay below 4 GiB
+    const size_t per_set = (size_t)8 * n * sizeof(double) + 10 * sizeof(double);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)P, (size_t(4) << 30) / per_set));
+    int rc = pl->gk.reserve((size_t)chunk * per_set);
+    if (rc) return rc;
+    double* planes = (double*)pl->gk.dev;
+    for (int p0 = 0; p0 < P; p0 += chunk) {
+        const int Pc = std::min(chunk, P - p0);
+        const size_t plane = (size_t)Pc * n;
+        double* bumped = planes + 8 * plane;  // [2][5][Pc]
+        const double* base = d_params + p0;
+        bump_v0_kernel<<<std::min((Pc + 127) / 128, pl->sm_count * 8), 128, 0, st>>>(base, ld, Pc, bumped);
+        g_launches++;
+        HB_CUDA(cudaGetLastError());
+        if ((rc = launch_jobs(pl, base, ld, Pc, W_PRICE, planes, nullptr, st))) return rc;
+        for (int i = 0; i < 5; ++i)
+            if ((rc = launch_jobs(pl->sib[i], base, ld, Pc, W_PRICE, planes + (size_t)(1 + i) * plane, nullptr, st)))
+                return rc;
+        if ((rc = launch_jobs(pl, bumped, Pc, Pc, W_PRICE, planes + 6 * plane, nullptr, st))) return rc;
+        if ((rc = launch_jobs(pl, bumped + (size_t)5 * Pc, Pc, Pc, W_PRICE, planes + 7 * plane, nullptr, st))) return rc;
+        const int grid = (int)std::min<size_t>((plane + 127) / 128, (size_t)pl->sm_count * 16);
+        greeks_combine_kernel<<<grid, 128, 0, st>>>(planes, plane, n, pl->d_maturity, pl->S.spot,
+                                                    d_greeks + (size_t)p0 * n * 5);
+        g_launches++;
+        HB_CUDA(cudaGetLastError());
+    }
     return HB_OK;
 }
 
@@ -577,6 +652,11 @@ int hb_price_host(hb_plan* pl, const double* h_params, int P, double* h_prices) 
 int hb_implied_vol_host(hb_plan* pl, const double* h_params, int P, double* h_iv) {
     const size_t n = pl && pl->has_surface ? (size_t)pl->S.n_opt : 0;
     return run_host(pl, h_params, P, 4 /* W_PRICE + implied-vol epilogue */, h_iv, (size_t)P * n, nullptr, 0);
+}
+int hb_greeks_host(hb_plan* pl, const double* h_params, int P, double* h_greeks) {
+    const size_t n = pl && pl->has_surface ? (size_t)pl->S.n_opt : 0;
+    return run_host(pl, h_params, P, 5 /* nine pricing passes + difference formulas */, h_greeks, (size_t)P * n * 5,
+                    nullptr, 0);
 }
 int hb_objective_host(hb_plan* pl, const double* h_params, int P, double* h_loss) {
     return run_host(pl, h_params, P, W_LOSS, h_loss, (size_t)P, nullptr, 0);

@@ -804,6 +804,44 @@ __global__ void implied_vol_kernel(const double* __restrict__ prices, const doub
 }
 
 // ============================================================================================
+// Finite-difference Greeks: HestonModel::price_option_with_greeks, heston.cpp:168-217.  The nine price
+// evaluations per option are nine launches of the pricing kernel on bumped surfaces / parameter sets;
+// these two kernels build the v0 +/- eps parameter sets and apply the difference formulas.
+// ============================================================================================
+
+constexpr double kEpsSpotRel = 0.001, kEpsRate = 0.0001, kEpsTime = 1.0 / 365.0, kEpsVol = 0.001;  // :175-178
+
+// out[0] = params with v0 + eps, out[1] = params with v0 - eps, both SoA [5][P]
+__global__ void bump_v0_kernel(const double* __restrict__ params, int ld, int P, double* __restrict__ out) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const double x = params[(size_t)c * ld + p];
+            out[(size_t)c * P + p] = (c == 4) ? x + kEpsVol : x;
+            out[(size_t)(5 + c) * P + p] = (c == 4) ? x - kEpsVol : x;
+        }
+    }
+}
+
+// pr = 8 price planes [8][P*n]: base, S+, S-, r+, r-, T-, v0+, v0-
+__global__ void greeks_combine_kernel(const double* __restrict__ pr, size_t plane, int n,
+                                      const double* __restrict__ maturity, double spot, double* __restrict__ out) {
+    const double eps_spot = spot * kEpsSpotRel;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const double price = pr[idx], up = pr[plane + idx], dn = pr[2 * plane + idx];
+        const double rup = pr[3 * plane + idx], rdn = pr[4 * plane + idx], later = pr[5 * plane + idx];
+        const double vup = pr[6 * plane + idx], vdn = pr[7 * plane + idx];
+        double* g = out + idx * 5;
+        g[0] = (up - dn) / (2.0 * eps_spot);                       // delta  :183
+        g[1] = (up - 2.0 * price + dn) / (eps_spot * eps_spot);    // gamma  :186
+        g[2] = (vup - vdn) / (2.0 * kEpsVol);                      // vega   :213
+        g[3] = (maturity[idx % n] > kEpsTime) ? (later - price) / kEpsTime : 0.0;  // theta :195-200
+        g[4] = (rup - rdn) / (2.0 * kEpsRate);                     // rho    :192
+    }
+}
+
+// ============================================================================================
 // K1 alone: characteristic function for arbitrary complex u
 // ============================================================================================
 

@@ -9,6 +9,8 @@ surface).  Batched counterparts of the reference's per-candidate calls:
 ``objective``          HestonCalibrator._compute_objective (heston_calibrator.py:486-513)
 ``jacobian``           _compute_residuals + SciPy 2-point Jacobian (heston_calibrator.py:515-536)
 ``normal_equations``   loss, ||r||^2, J^T r, triu(J^T J) per parameter set
+``implied_vol``        HestonModel::implied_volatility   (heston.cpp:311-349)
+``greeks``             HestonModel::price_option_with_greeks (heston.cpp:168-217)
 ``characteristic_function``  HestonModel::characteristic_function (heston.cpp:74-92)
 =====================  ==============================================================
 
@@ -142,6 +144,17 @@ class BatchPricer:
         check(self._L.hb_implied_vol(self._h, soa.data_ptr(), P, P, out.data_ptr(), st))
         return out
 
+    def greeks(self, params):
+        """[P, 5] -> finite-difference Greeks [P, n_options, 5] = delta, gamma, vega, theta, rho
+        (batched HestonModel::price_option_with_greeks, heston.cpp:168-217: same bumps, same formulas)."""
+        import torch
+
+        soa, st = self._soa(params)
+        P = soa.shape[1]
+        out = torch.empty((P, self.n_options, 5), dtype=torch.float64, device=params.device)
+        check(self._L.hb_greeks(self._h, soa.data_ptr(), P, P, out.data_ptr(), st))
+        return out
+
     def normal_equations(self, params):
         """[P, 5] -> [P, 22] = loss, ||r||^2, J^T r (5), triu(J^T J) (15)."""
         import torch
@@ -174,6 +187,12 @@ class BatchPricer:
         x = _np_d(np.atleast_2d(params))
         out = np.empty((x.shape[0], self.n_options))
         check(self._L.hb_implied_vol_host(self._h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def greeks_host(self, params) -> np.ndarray:
+        x = _np_d(np.atleast_2d(params))
+        out = np.empty((x.shape[0], self.n_options, 5))
+        check(self._L.hb_greeks_host(self._h, _ptr(x), x.shape[0], _ptr(out)))
         return out
 
     def objective_host(self, params) -> np.ndarray:

@@ -213,9 +213,34 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
     }
     // REFGRID
     {
-        const int max_ctas = 2 * pl->sm_count;
         const int slices = V * M;
-        const bool split = slices > 0 && (long long)P < 2LL * max_ctas && (size_t)P * row_bytes <= (size_t(1) << 30);
+        const size_t smem_rows = (size_t)P * row_bytes;
+        if (V == 6) {
+            // all six variants of a maturity resident: shared stages and twiddles (refgrid_job6_kernel);
+            // small batches run one job per (set, maturity)
+            static int rc6 = set_smem(refgrid_job6_kernel, kRef6Smem);
+            if (rc6) return rc6;
+            const int max_ctas = pl->sm_count;
+            const bool split = M > 0 && (long long)P < 2LL * max_ctas && smem_rows <= (size_t(1) << 30);
+            const long long n_jobs = split ? (long long)P * M : (long long)P;
+            const int grid = (int)std::max<long long>(1, std::min<long long>(n_jobs, max_ctas));
+            int rc = pl->scratch.reserve((size_t)(split ? P : grid) * row_bytes);
+            if (rc) return rc;
+            double* scratch = (double*)pl->scratch.dev;
+            refgrid_job6_kernel<<<grid, kRef6NT, kRef6Smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
+                                                                  scratch, split ? 1 : 0, ctr);
+            g_launches++;
+            HB_CUDA(cudaGetLastError());
+            if (split) {  // same block size as the in-kernel finalize: same reduction order, same bits
+                finalize_rows_kernel<kRef6NT><<<std::min(P, 4 * pl->sm_count), kRef6NT, 0, st>>>(
+                    S, pl->bd, d_params, ld, P, what, scratch, d_out, d_out2);
+                g_launches++;
+                HB_CUDA(cudaGetLastError());
+            }
+            return HB_OK;
+        }
+        const int max_ctas = 2 * pl->sm_count;
+        const bool split = slices > 0 && (long long)P < 2LL * max_ctas && smem_rows <= (size_t(1) << 30);
         const long long n_jobs = split ? (long long)P * slices : (long long)P;
         const int grid = (int)std::max<long long>(1, std::min<long long>(n_jobs, max_ctas));
         double* scratch = nullptr;

@@ -666,6 +666,14 @@ finalize_rows_kernel(SurfaceDev S, Bounds bd, const double* __restrict__ params,
 
 constexpr int kRefPoints = 1024;  // heston.cpp:126
 
+// Explicit FMA forms: both refgrid kernels must round identically whatever the compiler would contract.
+__device__ __forceinline__ cplx cmul_f(cplx a, cplx b) {
+    return {fma(a.re, b.re, -(a.im * b.im)), fma(a.re, b.im, a.im * b.re)};
+}
+__device__ __forceinline__ double re_mac(double acc, cplx t, double2 ps) {  // acc + Re(t * ps)
+    return fma(t.re, ps.x, fma(-t.im, ps.y, acc));
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 2)
 refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
@@ -739,14 +747,161 @@ refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restri
 #pragma unroll 4
                 for (int a = 0; a < kRefPoints / 32; ++a) {
                     const double2 ps = psi[lane + 32 * a];
-                    sum += twd.re * ps.x - twd.im * ps.y;
-                    twd = cmul(twd, st);
+                    sum = re_mac(sum, twd, ps);
+                    twd = cmul_f(twd, st);
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
                 if (lane == 0) {
                     const double call = S.opt_s0[o] * disc * (sum * du);  // heston.cpp:136-139
                     rows[(size_t)vnt * n + S.opt_orig[o]] = finish_price(call, S.opt_call[o] != 0, fwd, S.opt_kdisc[o]);
+                }
+            }
+            __syncthreads();
+        }
+        if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Six-variant refgrid kernel (normal equations / Jacobian, one CTA per parameter set).  All six
+// variants of one maturity are resident (6 x 16 KiB of psi), so
+//   * stage A is computed once per (set, class) and kept in thread-private local memory (4 classes x
+//     2 points), stage B once per (class, maturity) -- {base, theta', v0'} share it -- instead of
+//     A + B + F per slice: 4 B + 6 F per point and maturity instead of 6 (A + B + F);
+//   * the per-strike twiddle recurrence e^{-i v_j ln K} is advanced once and applied to the six
+//     psi vectors, and a warp sums two strikes per psi load (12 accumulators per lane).
+// Per slice and strike the arithmetic (operations and order) is that of refgrid_job_kernel, so the two
+// kernels agree to rounding (a few ulp: the compiler contracts the shared inline routines per call site).
+// --------------------------------------------------------------------------------------------
+
+constexpr int kRef6NT = 512;
+constexpr size_t kRef6Smem = (size_t)6 * kRefPoints * sizeof(double2);
+
+__global__ void __launch_bounds__(kRef6NT, 1)
+refgrid_job6_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
+                    double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int split,
+                    unsigned long long* job_counter) {
+    constexpr int NT = kRef6NT, PTS = kRefPoints / NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* psi = reinterpret_cast<double2*>(smem_raw);  // [6][kRefPoints]
+    __shared__ long long s_job;
+    __shared__ JobState js;
+    __shared__ double red[(NT / 32) * 23];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = S.n_opt, M = S.n_mat;
+    const double du = 0.01;  // heston.cpp:127
+    // class c -> variants sharing its (kappa, sigma, rho): 0 {base, theta', v0'}, kappa', sigma', rho'
+    const int cls_variant[4] = {0, 1, 3, 4};
+
+    auto next_job = [&](long long cur) -> long long {  // dynamic queue, as in fft_job_kernel
+        if (!job_counter) return cur + gridDim.x;
+        __syncthreads();
+        if (tid == 0) s_job = (long long)gridDim.x + (long long)atomicAdd(job_counter, 1ULL);
+        __syncthreads();
+        return s_job;
+    };
+    // split = one job per (set, maturity) with rows in global memory and a separate finalize kernel
+    // (small P: fills the SMs); otherwise one job per set, finalized in place.
+    const long long n_jobs = split ? (long long)P * M : (long long)P;
+    for (long long job = blockIdx.x; job < n_jobs; job = next_job(job)) {
+        const int p = split ? (int)(job / M) : (int)job;
+        const int mat_begin = split ? (int)(job % M) : 0, mat_end = split ? mat_begin + 1 : M;
+        __syncthreads();
+        if (tid == 0) job_setup(js, params, ld, p, bd, 6);
+        __syncthreads();
+        if (!js.valid) {
+            if (!split) invalid_job<NT>(what, S, p, out, out2, tid);
+            continue;
+        }
+        double* rows = scratch + (size_t)(split ? p : (int)blockIdx.x) * 6 * n;
+        if (mat_begin == 0) {
+            for (int v = 0; v < 6; ++v)
+                for (int i = tid; i < S.n_intr; i += NT) rows[(size_t)v * n + S.intr_orig[i]] = S.intr_val[i];
+        }
+        // stage A per (class, point) and the Carr-Madan denominator per point
+        StageA ac[4][PTS];
+        cplx den[PTS];
+#pragma unroll
+        for (int k = 0; k < PTS; ++k) {
+            const int j = tid + k * NT;
+            const double v = (double)j * du;
+            den[k] = cm_inv_denominator(v, gc.alpha);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double* x = js.x[cls_variant[c]];
+                const ClassConst cc = {x[0], x[2] * x[2], x[3] * x[2]};
+                ac[c][k] = stage_a(cc, v, gc.ui);
+            }
+        }
+        for (int mat = mat_begin; mat < mat_end; ++mat) {
+            const double T = S.mat_T[mat];
+            const double lsm = S.ln_spot + (S.rate - S.dividend) * T;
+#pragma unroll 1
+            for (int k = 0; k < PTS; ++k) {
+                const int j = tid + k * NT;
+                const double v = (double)j * du;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const StageB b = stage_b(ac[c][k], T);
+                    const int nv = (c == 0) ? 3 : 1;
+                    for (int i = 0; i < nv; ++i) {
+                        const int vnt = (c == 0) ? (i == 0 ? 0 : (i == 1 ? 2 : 5)) : cls_variant[c];
+                        const double* x = js.x[vnt];
+                        const double s2 = x[2] * x[2];
+                        const SliceConst sc = {x[0] * x[1] / s2, x[4] / s2, lsm};
+                        cplx r = {0.0, 0.0};  // integrand(0) == 0, heston.cpp:110
+                        if (j > 0) r = cmul(stage_f(b, sc, v, gc.ui), den[k]);
+                        psi[vnt * kRefPoints + j] = make_double2(r.re, r.im);
+                    }
+                }
+            }
+            __syncthreads();
+            const double disc = S.mat_disc[mat], fwd = S.mat_fwd[mat];
+            const int o0 = S.mat_off[mat], o1 = S.mat_off[mat + 1];
+            // a warp sums two strikes at a time over the six resident psi vectors
+            for (int ob = o0 + 2 * warp; ob < o1; ob += 2 * (NT / 32)) {
+                const bool two = ob + 1 < o1;
+                const double k0 = S.opt_lnk[ob], k1 = S.opt_lnk[two ? ob + 1 : ob];
+                // e^{-i v_j k}, j = lane + 32 a: base rotation times a 32-step recurrence
+                double sb, cb, ss, cs;
+                sincos_nb(-((double)lane * du) * k0, &sb, &cb);
+                sincos_nb(-(32.0 * du) * k0, &ss, &cs);
+                cplx tw0 = {cb, sb};
+                const cplx st0 = {cs, ss};
+                sincos_nb(-((double)lane * du) * k1, &sb, &cb);
+                sincos_nb(-(32.0 * du) * k1, &ss, &cs);
+                cplx tw1 = {cb, sb};
+                const cplx st1 = {cs, ss};
+                double sum0[6], sum1[6];
+#pragma unroll
+                for (int v = 0; v < 6; ++v) sum0[v] = sum1[v] = 0.0;
+#pragma unroll 2
+                for (int a = 0; a < kRefPoints / 32; ++a) {
+#pragma unroll
+                    for (int v = 0; v < 6; ++v) {
+                        const double2 ps = psi[v * kRefPoints + lane + 32 * a];
+                        sum0[v] = re_mac(sum0[v], tw0, ps);
+                        sum1[v] = re_mac(sum1[v], tw1, ps);
+                    }
+                    tw0 = cmul_f(tw0, st0);
+                    tw1 = cmul_f(tw1, st1);
+                }
+#pragma unroll
+                for (int v = 0; v < 6; ++v) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        sum0[v] += __shfl_xor_sync(0xffffffffu, sum0[v], off);
+                        sum1[v] += __shfl_xor_sync(0xffffffffu, sum1[v], off);
+                    }
+                }
+                if (lane < 12 && (lane < 6 || two)) {
+                    const int v = lane % 6, o = ob + lane / 6;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) sum = (v == i) ? (lane < 6 ? sum0[i] : sum1[i]) : sum;
+                    const double call = S.opt_s0[o] * disc * (sum * du);  // heston.cpp:136-139
+                    rows[(size_t)v * n + S.opt_orig[o]] = finish_price(call, S.opt_call[o] != 0, fwd, S.opt_kdisc[o]);
                 }
             }
             __syncthreads();

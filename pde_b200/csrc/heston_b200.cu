@@ -184,17 +184,23 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
             scratch = (double*)pl->scratch.dev;
         }
         const size_t smem = job_smem_bytes(pl->Nsub, gmax);
+#define HB_LAUNCH_JOB(NN, NTT, DEC, ONE)                                                                       \
+    fft_job_kernel<NN, NTT, DEC, ONE><<<grid, NTT, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, \
+                                                               scratch, gmax, split ? 1 : 0, ctr)
+        const bool one = (V == 1);
         if (pl->Nsub == 4096) {
-            if (pl->R == 1)
-                fft_job_kernel<4096, kNT4096, false><<<grid, kNT4096, smem, st>>>(
-                    S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0, ctr);
-            else
-                fft_job_kernel<4096, kNT4096, true><<<grid, kNT4096, smem, st>>>(
-                    S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, gmax, split ? 1 : 0, ctr);
+            if (pl->R == 1) {
+                if (one) HB_LAUNCH_JOB(4096, kNT4096, false, true);
+                else HB_LAUNCH_JOB(4096, kNT4096, false, false);
+            } else {
+                if (one) HB_LAUNCH_JOB(4096, kNT4096, true, true);
+                else HB_LAUNCH_JOB(4096, kNT4096, true, false);
+            }
         } else {
-            fft_job_kernel<512, kNT512, false><<<grid, kNT512, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2,
-                                                             scratch, gmax, split ? 1 : 0, ctr);
+            if (one) HB_LAUNCH_JOB(512, kNT512, false, true);
+            else HB_LAUNCH_JOB(512, kNT512, false, false);
         }
+#undef HB_LAUNCH_JOB
         g_launches++;
         HB_CUDA(cudaGetLastError());
         if (split && what != W_PRICE) {
@@ -352,9 +358,17 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     std::memcpy(pl->bd.lb, lb, sizeof lb);
     std::memcpy(pl->bd.ub, ub, sizeof ub);
     if (mode == HB_MODE_FFT) {
-        int rc = (n_grid > 4096)    ? set_smem(fft_job_kernel<4096, kNT4096, true>, job_smem_bytes(4096, gmax_for(4096)))
-                 : (n_grid == 4096) ? set_smem(fft_job_kernel<4096, kNT4096, false>, job_smem_bytes(4096, gmax_for(4096)))
-                                    : set_smem(fft_job_kernel<512, kNT512, false>, job_smem_bytes(512, gmax_for(512)));
+        int rc = HB_OK;
+        if (n_grid > 4096) {
+            rc = set_smem(fft_job_kernel<4096, kNT4096, true, true>, job_smem_bytes(4096, gmax_for(4096)));
+            if (!rc) rc = set_smem(fft_job_kernel<4096, kNT4096, true, false>, job_smem_bytes(4096, gmax_for(4096)));
+        } else if (n_grid == 4096) {
+            rc = set_smem(fft_job_kernel<4096, kNT4096, false, true>, job_smem_bytes(4096, gmax_for(4096)));
+            if (!rc) rc = set_smem(fft_job_kernel<4096, kNT4096, false, false>, job_smem_bytes(4096, gmax_for(4096)));
+        } else {
+            rc = set_smem(fft_job_kernel<512, kNT512, false, true>, job_smem_bytes(512, gmax_for(512)));
+            if (!rc) rc = set_smem(fft_job_kernel<512, kNT512, false, false>, job_smem_bytes(512, gmax_for(512)));
+        }
         if (rc) {
             delete pl;
             return rc;

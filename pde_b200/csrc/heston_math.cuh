@@ -210,6 +210,41 @@ HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui, d
     return phi;
 }
 
+// ---- decayed tail: a rigorous bound that needs no stage B ------------------------------------------
+// stage_f returns exactly (0, 0) when er = Re(exponent) < -746 (exp underflows).  On the Carr-Madan grid
+// that is ~40 % of all (point, maturity) pairs, and stage B (a cexp and a clog) is what tells.  The bound
+// below decides most of them from stage A alone.  With E = |e| = exp(-Re d T), and |g| <= 2:
+//   Re B  = Re(num) T - 2 log|1 - g e| + 2 log|1 - g|  <=  Re(num) T + l1g + 4E/(1-2E)
+//           (|log|1-x|| <= |x|/(1-|x|), |x| = |g| E <= 2E;   l1g = 2 log|1 - g|)
+//   Re Dq = Re(num) + Re(num (g-1) e/(1 - g e))        <=  Re(num) + |num| 3E/(1-2E)
+// so for kappa theta/sigma^2 >= 0, v0/sigma^2 >= 0 and Re d T > 5 (E < e^-5)
+//   er <= kts (Re(num) T + l1g + c1) + v0s (Re(num) + c2 |num|_1) - ui lsm =: ub,
+// and ub < -750 implies that the computed er is below -746 (the 4 units of slack dwarf the rounding of
+// B and Dq, ~1e-9 here) -- the slice's value at the point is exactly 0 and stage B / F are not evaluated.
+// tests/test_host_math.py checks implication and coverage (89 % of the underflowed pairs) on the box.
+HB_HD double tail_l1g(const StageA& a) {
+    const double g2 = a.g.re * a.g.re + a.g.im * a.g.im;
+    const double l = log1p_nb(fma_(-2.0, a.g.re, g2));  // log|1 - g|^2
+    return (g2 <= 4.0) ? l : HUGE_VAL;                   // premise |g| <= 2 (NaN -> inf: never dead)
+}
+// Point part of the bound (shared by the slices of a group) and slice part.
+struct TailPoint {
+    double dre, nre, cD;  // Re d, Re(num), Re(num) + c2 |num|_1
+};
+HB_HD TailPoint tail_point(const StageA& a) {
+    const double c2 = 0.02049;  // 3E/(1-2E) = 0.0204899..., E = e^-5, rounded up
+    return {a.d.re, a.num.re, fma_(c2, fabs(a.num.re) + fabs(a.num.im), a.num.re)};
+}
+// Upper bound of er, or +inf when the premises fail (NaN inputs compare false -> +inf: never dead).
+HB_HD double tail_ub(const TailPoint& t, double l1g, double T, double kts, double v0s, double lsm, double ui) {
+    const double c1 = 0.02732;  // 4E/(1-2E) = 0.0273199..., rounded up
+    const double ub = kts * (fma_(t.nre, T, l1g) + c1) + v0s * t.cD - ui * lsm;
+    return ((t.dre * T > 5.0) && (kts >= 0.0) && (v0s >= 0.0)) ? ub : HUGE_VAL;
+}
+HB_HD bool tail_dead(const StageA& a, double l1g, double T, double kts, double v0s, double lsm, double ui) {
+    return tail_ub(tail_point(a), l1g, T, kts, v0s, lsm, ui) < -750.0;
+}
+
 // Full CF for arbitrary complex u (the bound API characteristic_function(u,T,S0,r,q)).
 HB_HD cplx heston_cf(double kappa, double theta, double sigma, double rho, double v0, double ur, double ui,
                      double T, double S0, double r, double q) {

@@ -46,3 +46,16 @@ extern "C" void hm_cf_exponent(const double* p, int n, const double* ur, double 
         hb::stage_f(b, s, ur[j], ui, er + j);
     }
 }
+
+// decayed-tail bound of heston_math.cuh next to the exponent stage F computes: dead[j] = tail_dead(...)
+extern "C" void hm_tail_bound(const double* p, int n, const double* ur, double ui, double T, double S0, double r,
+                              double q, double* er, int* dead) {
+    hb::ClassConst c = {p[0], p[2] * p[2], p[3] * p[2]};
+    hb::SliceConst s = {p[0] * p[1] / c.sigma2, p[4] / c.sigma2, log(S0) + (r - q) * T};
+    for (int j = 0; j < n; ++j) {
+        hb::StageA a = hb::stage_a(c, ur[j], ui);
+        hb::StageB b = hb::stage_b(a, T);
+        hb::stage_f(b, s, ur[j], ui, er + j);
+        dead[j] = hb::tail_dead(a, hb::tail_l1g(a), T, s.kts, s.v0s, s.lsm, ui) ? 1 : 0;
+    }
+}

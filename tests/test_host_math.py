@@ -199,3 +199,33 @@ def test_tail_skip_margin(hm):
                     worst_rel = max(worst_rel, float(np.max(np.abs(ek - e0)[dead] / np.abs(e0[dead]))))
     assert flagged > 0.2 * len(X) * 3 * v.size  # the regime is common: > 20 % of all grid points
     assert worst_rel < 1e-4  # vs the 6.7 % (54/800) it would take to break the skip
+
+
+def test_tail_bound_is_rigorous_and_useful(hm):
+    """heston_math.cuh tail_dead(): decides from stage A alone (no cexp, no clog) that Re(exponent) < -746,
+    i.e. that stage F would return exactly 0.  Implication must hold on every grid point of every set
+    (Sobol + all box corners, FD-perturbed variants included); coverage shows the bound is worth having."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from bench import fd_variants
+    from scipy.stats import qmc
+
+    corners = [np.where([(m >> b) & 1 for b in range(5)], UB, LB) for m in range(32)]
+    X = np.vstack([LB + (UB - LB) * qmc.Sobol(d=5, seed=11).random(128), corners])
+    v = 0.25 * np.arange(4096.0)
+    n_dead = n_caught = 0
+    for x in X:
+        for p in fd_variants(x[None, :])[[0, 1, 3, 4]]:  # base, kappa', sigma', rho'
+            p = np.ascontiguousarray(p, dtype=float)
+            for T in (0.1, 0.55, 1.0, 2.0):
+                er = np.empty(v.size)
+                dead = np.zeros(v.size, dtype=np.int32)
+                hm.hm_tail_bound(_p(p), C.c_int(v.size), _p(v), C.c_double(-1.75), C.c_double(T), C.c_double(S0),
+                                 C.c_double(R), C.c_double(Q), _p(er), dead.ctypes.data_as(C.POINTER(C.c_int)))
+                flagged = dead.astype(bool)
+                assert (er[flagged] < -749.0).all(), (p, T, er[flagged].max())  # 3 of the 4 units of slack unused
+                n_dead += int((er < -746.0).sum())
+                n_caught += int(flagged.sum())
+    assert n_dead > 0 and n_caught > 0.8 * n_dead, (n_caught, n_dead)
+

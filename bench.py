@@ -170,14 +170,27 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def measured_traffic(P):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the bench step, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json); null when the launch shape differs."""
+def _ncu_capture(P):
+    """The committed `ncu --set full` capture of ONE launch of the bench step (profiles/r01_traffic.json);
+    None when the launch shape differs."""
     path = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(path):
         return None
     t = json.load(open(path))
-    return t["dram_bytes_per_launch"] if (t["sets_per_launch"], t["maturities"], t["strikes"]) == (P, N_MAT, N_STRIKE) else None
+    return t if (t["sets_per_launch"], t["maturities"], t["strikes"]) == (P, N_MAT, N_STRIKE) else None
+
+
+def measured_traffic(P):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, or null."""
+    t = _ncu_capture(P)
+    return t["dram_bytes_per_launch"] if t else None
+
+
+def ncu_pipe_active(P):
+    """sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of that capture as a fraction, or null:
+    the executed-work utilisation next to the algorithmic (W1) fraction, which sharing pushes above 1."""
+    t = _ncu_capture(P)
+    return t["fp64_pipe_active_pct"] / 100.0 if t else None
 
 
 def workload_config(P):
@@ -287,6 +300,7 @@ def run_ours(args):
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": measured_traffic(P),
+                         "fp64_pipe_active_ncu": ncu_pipe_active(P),
                          "peak_source": "DFMA probe (hb_measure_fp64_peak) run in this process; "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_slice_W1": FLOPS_PER_SLICE,

@@ -197,8 +197,9 @@ struct SliceConst {
 
 // phi = exp(C + D v0 + i u (ln S0 + (r-q)T)),  i u = (-ui, ur)        heston.cpp:87-91
 HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui, double* er_out = nullptr) {
-    const double er = s.kts * b.B.re + s.v0s * b.Dq.re - ui * s.lsm;
-    const double ei = s.kts * b.B.im + s.v0s * b.Dq.im + ur * s.lsm;
+    // explicit FMA order: the fused kernel restates these two lines inline (cexp_w<3> path) and must round alike
+    const double er = fma_(s.kts, b.B.re, fma_(s.v0s, b.Dq.re, -(ui * s.lsm)));
+    const double ei = fma_(s.kts, b.B.im, fma_(s.v0s, b.Dq.im, ur * s.lsm));
     if (er_out) *er_out = er;  // log|phi|, used by the caller's decayed-tail bookkeeping
     // exp(er) underflows to exactly 0 below -745.14: the result is (+-0, +-0) whatever the phase, so the
     // cexp is skipped -- bit-identical output (sign of zero aside).  On the calibrator's box ~40 % of the

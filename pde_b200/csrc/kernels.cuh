@@ -571,8 +571,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
 #pragma unroll
                         for (int g = 0; g < 3; ++g) {
                             const SubSlice& s = grp.s[g];
-                            er[g] = s.kts * b.B.re + s.v0s * b.Dq.re - gc.ui * s.lsm;  // stage_f, heston.cpp:87-91
-                            ei[g] = s.kts * b.B.im + s.v0s * b.Dq.im + v * s.lsm;
+                            er[g] = fma(s.kts, b.B.re, fma(s.v0s, b.Dq.re, -(gc.ui * s.lsm)));  // stage_f, heston.cpp:87-91
+                            ei[g] = fma(s.kts, b.B.im, fma(s.v0s, b.Dq.im, v * s.lsm));
                         }
                         dmask |= (er[0] < -800.0 ? 1u : 0u) << k;
                         double pr[3] = {0.0, 0.0, 0.0}, pi[3] = {0.0, 0.0, 0.0};

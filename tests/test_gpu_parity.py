@@ -361,3 +361,43 @@ def test_full_size_objective_properties(torch_cuda, oracle):
     if odd.size:
         want_odd = oracle.objective_batch(MODE_FFT, params[odd], Kf, Tf, True, mk, S0, R, Q)
         assert np.array_equal(all_loss[odd], want_odd, equal_nan=True), (params[odd], all_loss[odd], want_odd)
+
+
+def test_full_size_normal_equations_properties(torch_cuda):
+    """BASELINE.json config 3 at full size (65,536 sets x 32 maturities x 50 strikes, FD blocks): properties
+    that do not need the oracle.  The six-variant kernel (dead masks, cexp_w<3>) and the one-variant kernel
+    (rigorous tail bound) are different instantiations with different work elision: the loss column of the
+    normal equations must still be the objective's loss bit for bit."""
+    from pde_b200 import BatchPricer
+
+    torch = torch_cuda
+    P = 65536
+    X = _dev(torch, sobol_sets(P))
+    Kf, Tf = np.tile(np.linspace(80, 120, 50), 32), np.repeat(np.linspace(0.1, 1.0, 32), 50)
+    pr = BatchPricer("fft").set_surface(Kf, Tf, True, None, S0=S0, r=R, q=Q)
+    mk = pr.price(_dev(torch, [DEFAULT])).cpu().numpy()[0]
+    mk = np.maximum(mk * (1 + 0.001 * np.random.default_rng(42).normal(size=mk.size)), 0.01)
+    pr.set_surface(Kf, Tf, True, mk, S0=S0, r=R, q=Q).set_bounds(LB, UB)
+    neq = pr.normal_equations(X)
+    loss = pr.objective(X)
+    a, b = neq[:, 0].cpu().numpy(), loss.cpu().numpy()
+    assert np.array_equal(np.isfinite(a), np.isfinite(b)) and np.array_equal(a == 1e10, b == 1e10)
+    ok = np.isfinite(a)
+    dev = np.max(np.abs(a[ok] - b[ok]) / np.abs(b[ok]))
+    assert dev == 0.0, dev
+    # determinism and permutation equivariance of all 22 columns
+    perm = torch.randperm(P, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(2))
+    assert torch.equal(pr.normal_equations(X[perm]).view(torch.int64), neq[perm].view(torch.int64))  # NaN-safe
+    # ||r||^2 >= 0, diag(J^T J) >= 0, Cauchy-Schwarz |(J^T J)_ab| <= sqrt((J^T J)_aa (J^T J)_bb) wherever finite
+    n = neq.cpu().numpy()
+    fin = np.isfinite(n).all(axis=1)
+    assert fin.mean() > 0.9
+    n = n[fin]
+    iu = np.triu_indices(5)
+    A = np.zeros((len(n), 5, 5))
+    A[:, iu[0], iu[1]] = n[:, 7:]
+    d = np.sqrt(np.einsum("pii->pi", A))
+    assert (n[:, 1] >= 0).all() and (np.einsum("pii->pi", A) >= 0).all()
+    assert (np.abs(A[:, iu[0], iu[1]]) <= d[:, iu[0]] * d[:, iu[1]] * (1 + 1e-12) + 1e-300).all()
+    # |J^T r| <= ||J_a|| ||r||
+    assert (np.abs(n[:, 2:7]) <= d * np.sqrt(n[:, 1])[:, None] * (1 + 1e-12) + 1e-300).all()

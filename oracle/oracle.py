@@ -181,6 +181,42 @@ class Oracle:
         return out
 
 
+def _sabr_args(K, params):
+    K_, kp = _d(np.atleast_1d(K))
+    x_, xp = _d(np.atleast_2d(params))
+    if x_.shape[1] != 3:
+        raise ValueError("SABR parameter rows are (alpha, rho, nu)")
+    return K_, kp, x_, xp
+
+
+class SabrOracle:
+    """C restatement (oracle/sabr_oracle.c) of the reference's two SABR formulas: flavour "cpp" =
+    SABRModel::implied_volatility (sabr.cpp:130-192), "py" = SABRCalibrator.sabr_implied_vol
+    (sabr_calibrator.py:159-258) and the calibration objective (:316-324)."""
+
+    def __init__(self, path: str | None = None):
+        path = path or os.path.join(HERE, "liborc.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        self.lib = C.CDLL(path)
+
+    def vols(self, flavour: str, beta, F, T, K, params) -> np.ndarray:
+        K_, kp, x_, xp = _sabr_args(K, params)
+        out = np.empty((x_.shape[0], K_.size))
+        self.lib.orc_sabr_vols(C.c_int({"cpp": 0, "py": 1}[flavour]), C.c_double(beta), C.c_double(F), C.c_double(T),
+                               C.c_int(K_.size), kp, C.c_int(x_.shape[0]), xp, out.ctypes.data_as(_dp))
+        return out
+
+    def objective(self, beta, F, T, K, market, weights, params) -> np.ndarray:
+        K_, kp, x_, xp = _sabr_args(K, params)
+        m_, mp = _d(market)
+        w_, wp = _d(weights)
+        out = np.empty(x_.shape[0])
+        self.lib.orc_sabr_objective(C.c_double(beta), C.c_double(F), C.c_double(T), C.c_int(K_.size), kp, mp, wp,
+                                    C.c_int(x_.shape[0]), xp, out.ctypes.data_as(_dp))
+        return out
+
+
 class Reference:
     """The reference's own heston.cpp (unmodified) behind oracle/ref_shim.cpp."""
 
@@ -263,6 +299,14 @@ class Reference:
         self._chk(self.lib.ref_implied_vol(pp, C.c_double(K), C.c_double(T), C.c_double(S0), C.c_double(r),
                                            C.c_double(q), int(bool(is_call)), C.byref(out)))
         return out.value
+
+    def sabr_vols(self, beta, F, T, K, params) -> np.ndarray:
+        """The reference's SABRModel::implied_volatility (sabr.cpp compiled unmodified); NaN where it throws."""
+        K_, kp, x_, xp = _sabr_args(K, params)
+        out = np.empty((x_.shape[0], K_.size))
+        self.lib.ref_sabr_vols(C.c_double(beta), C.c_double(F), C.c_double(T), C.c_int(K_.size), kp,
+                               C.c_int(x_.shape[0]), xp, out.ctypes.data_as(_dp))
+        return out
 
     def greeks(self, p, K, T, S0, r, q, is_call=True) -> np.ndarray:
         p_, pp = _d(p)

@@ -12,6 +12,7 @@
 //   ref_price_options -> HestonModel::price_options           (heston.cpp:220-245, OpenMP)
 //   ref_implied_vol   -> HestonModel::implied_volatility      (heston.cpp:311-349)
 //   ref_greeks        -> HestonModel::price_option_with_greeks(heston.cpp:169-218)
+//   ref_sabr_vols     -> SABRModel::implied_volatility        (sabr.cpp:130-192); NaN where it throws
 #include <cmath>
 #include <complex>
 #include <cstdint>
@@ -22,6 +23,7 @@
 #include <vector>
 
 #include "models/heston.hpp"
+#include "models/sabr.hpp"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -170,4 +172,17 @@ int ref_num_threads() {
 #endif
 }
 
+
+// vols[p * n + i] for P rows (alpha, rho, nu) and n strikes through the reference's SABRModel
+void ref_sabr_vols(double beta, double F, double T, int n, const double* K, int P, const double* params, double* vols) {
+    quant::models::SABRModel m(beta);
+    for (int p = 0; p < P; ++p)
+        for (int i = 0; i < n; ++i) {
+            try {
+                vols[(size_t)p * n + i] = m.implied_volatility(K[i], F, T, params[3 * p], params[3 * p + 1], params[3 * p + 2]);
+            } catch (const std::exception&) {
+                vols[(size_t)p * n + i] = std::numeric_limits<double>::quiet_NaN();
+            }
+        }
+}
 }  // extern "C"

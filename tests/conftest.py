@@ -60,6 +60,11 @@ def g_cal():
 
 
 @pytest.fixture(scope="session")
+def g_sabr():
+    return load_golden("ref_sabr.npz")
+
+
+@pytest.fixture(scope="session")
 def g_fft():
     return load_golden("fft_selfcheck.npz")
 

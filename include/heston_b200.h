@@ -127,6 +127,35 @@ int hb_fft_batch(double* d_data, int n, int n_slices, void* stream);
 
 int hb_sync(void* stream);
 
+/* ---- SABR (Hagan 2002) smile path: the sibling hot loop ------------------------
+ * The reference holds two formulas that differ in their guards; `flavour` selects which is restated:
+ *   HB_SABR_CPP  SABRModel::implied_volatility (src/cpp/models/sabr.cpp:130-192; bound as
+ *                quant_cpp.sabr.SABRModel.implied_volatility / implied_volatilities, bindings/sabr_bindings.cpp);
+ *                NaN where the reference throws std::invalid_argument
+ *   HB_SABR_PY   SABRCalibrator.sabr_implied_vol (calibration/sabr_calibrator.py:159-258), what the
+ *                calibration objective evaluates
+ * Parameter sets are SoA: d_params[c * ld + p], c = alpha, rho, nu; beta is fixed per call (sabr.cpp:19-32). */
+#define HB_SABR_CPP 0
+#define HB_SABR_PY 1
+
+/* d_vols[p * n + i] for P parameter sets on one smile (forward, maturity, n strikes): replaces a loop of
+ * implied_volatility / SABRModel::implied_volatilities (sabr.cpp:194-207). */
+int hb_sabr_vols(int flavour, double beta, double forward, double maturity, int n, const double* d_strikes,
+                 const double* d_params, int ld, int P, double* d_vols, void* stream);
+
+/* Calibration objective of calibrate_single_maturity (sabr_calibrator.py:316-324) for every (smile, candidate):
+ * d_loss[m * P + p] = sum_i w_i (sigma_i - market_i)^2, smiles in CSR form (d_off[n_smiles + 1] into d_strikes /
+ * d_market / d_weights, weights already normalised as in :291-293; at most max_strikes <= 512 per smile),
+ * candidates d_params[(m * 3 + c) * ld + p].  One launch for all maturities x candidates instead of one
+ * Python formula evaluation per (candidate, strike). */
+int hb_sabr_objective(double beta, int n_smiles, const double* d_forward, const double* d_maturity, const int* d_off,
+                      int max_strikes, const double* d_strikes, const double* d_market, const double* d_weights,
+                      const double* d_params, int ld, int P, double* d_loss, void* stream);
+
+/* Host-pointer variant of hb_sabr_vols: h_params AoS double[P][3]; copies included. */
+int hb_sabr_vols_host(int flavour, double beta, double forward, double maturity, int n, const double* h_strikes,
+                      const double* h_params, int P, double* h_vols);
+
 /* ---- host-pointer entry points (what a pybind11 / ctypes binding calls) --------------------
  * h_params is AoS double[P][5].  Each call copies inputs to the device, runs the same kernels
  * as above and copies the result back before returning. */

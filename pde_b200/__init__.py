@@ -7,8 +7,10 @@ Layout (only what the path needs):
   cpp/          quant_cpp-compatible module object (reference: src/cpp/bindings)
   models/       HestonModel wrapper with the reference's API (reference: models/heston.py)
   calibration/  HestonCalibrator with the reference's API + batched drivers
+  sabr.py       BatchSABR: batched SABR vols / smile objective
   sharding.py   parameter-set sharding across GPUs + loss all-gather
 """
+from .sabr import BatchSABR  # noqa: F401
 from .pricer import BatchPricer, characteristic_function, fft_batch, launch_count, measure_fp64_peak  # noqa: F401
 
 __version__ = "0.1.0"

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("PDE_B200_LIB") or os.path.join(HERE, "csrc", "libhest
 HB_OK, HB_ERR_INVALID_ARGUMENT, HB_ERR_INVALID_PARAMETER, HB_ERR_CUDA, HB_ERR_STATE = range(5)
 HB_MODE_REFGRID, HB_MODE_FFT = 0, 1
 HB_NEQ_WIDTH = 22
+HB_SABR_CPP, HB_SABR_PY = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
@@ -53,6 +54,10 @@ SIGNATURES = {
                               C.c_int]),
     "hb_model_price_options": (C.c_int, [_dp, C.c_int, _dp, C.c_int, _dp, C.c_double, C.c_double, C.c_double, C.c_int,
                                          _dp, C.c_int]),
+    "hb_sabr_vols": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "hb_sabr_objective": (C.c_int, [C.c_double, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
+                                    _vp, _vp]),
+    "hb_sabr_vols_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp, C.c_int, _dp]),
     "hb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, _dp]),
     "hb_launch_count": (C.c_uint64, []),
 }

@@ -11,7 +11,8 @@ the GPU in "refgrid" mode, i.e. they return what the reference returns (heston.c
 ``price_option_with_greeks`` and ``implied_volatility`` are the reference's host-side recipes
 (heston.cpp:169-218, :275-349) over those GPU prices.
 
-SABR / OU / PDE submodules are out of scope and absent.
+``quant_cpp.sabr`` (SABRModel, SABRParameters) evaluates the reference's Hagan formula on
+the device through ``hb_sabr_vols``.  OU / PDE submodules are out of scope and absent.
 """
 from __future__ import annotations
 
@@ -215,3 +216,104 @@ heston.OptionGreeks = OptionGreeks
 heston.PricingResult = PricingResult
 heston.HestonParameters = HestonParameters
 heston.HestonModel = HestonModel
+
+
+# ---- quant_cpp.sabr: SABRModel (src/cpp/bindings/sabr_bindings.cpp, src/cpp/models/sabr.cpp) ----------------
+
+class SABRParameters:
+    """sabr.hpp:14-62 (defaults: typical equity parameters)."""
+
+    def __init__(self, alpha: float = 0.2, beta: float = 0.5, rho: float = -0.3, nu: float = 0.4):
+        self.alpha, self.beta, self.rho, self.nu = float(alpha), float(beta), float(rho), float(nu)
+
+    def is_valid(self) -> bool:
+        return self.alpha > 0.0 and 0.0 <= self.beta <= 1.0 and abs(self.rho) < 1.0 and self.nu >= 0.0
+
+    def validate(self) -> None:
+        if not self.alpha > 0.0:
+            raise ValueError("SABR: alpha must be positive, got %f" % self.alpha)
+        if not 0.0 <= self.beta <= 1.0:
+            raise ValueError("SABR: beta must be in [0, 1], got %f" % self.beta)
+        if not abs(self.rho) < 1.0:
+            raise ValueError("SABR: |rho| must be < 1, got %f" % self.rho)
+        if not self.nu >= 0.0:
+            raise ValueError("SABR: nu must be non-negative, got %f" % self.nu)
+
+    def __repr__(self) -> str:
+        return "SABRParameters(alpha=%f, beta=%f, rho=%f, nu=%f)" % (self.alpha, self.beta, self.rho, self.nu)
+
+
+class SABRModel:
+    """Drop-in for ``quant_cpp.sabr.SABRModel``: same names, keyword arguments and exceptions; the formula
+    (sabr.cpp:34-192) is evaluated on the device through ``hb_sabr_vols`` (flavour HB_SABR_CPP)."""
+
+    def __init__(self, beta: float = 0.5):
+        self._set_beta(beta)
+
+    def _set_beta(self, beta: float) -> None:  # sabr.cpp:19-32
+        if beta < 0.0 or beta > 1.0:
+            raise ValueError("SABR: beta must be in [0, 1], got %f" % beta)
+        self._beta = float(beta)
+
+    beta = property(lambda self: self._beta, _set_beta)
+
+    @staticmethod
+    def _check(strike, forward, maturity, alpha, rho, nu) -> None:  # the reference's throws, sabr.cpp:132-150
+        if strike is not None and not strike > 0.0:
+            raise ValueError("SABR: strike must be positive")
+        if not forward > 0.0:
+            raise ValueError("SABR: forward must be positive")
+        if not alpha > 0.0:
+            raise ValueError("SABR: alpha must be positive")
+        if not abs(rho) < 1.0:
+            raise ValueError("SABR: |rho| must be < 1")
+        if not nu >= 0.0:
+            raise ValueError("SABR: nu must be non-negative")
+        if not maturity >= 0.0:
+            raise ValueError("SABR: maturity must be non-negative")
+
+    def _vols(self, strikes, forward, maturity, alpha, rho, nu) -> np.ndarray:
+        K, kp = _arr(strikes)
+        x, xp = _arr([alpha, rho, nu])
+        out = np.empty(K.size)
+        check(_lib.load().hb_sabr_vols_host(_lib.HB_SABR_CPP, self._beta, float(forward), float(maturity), K.size, kp, xp,
+                                            1, out.ctypes.data_as(_dp)))
+        return out
+
+    def implied_volatility(self, strike: float, forward: float, maturity: float, alpha=None, rho=None, nu=None,
+                           params: "SABRParameters" = None) -> float:
+        if params is not None or isinstance(alpha, SABRParameters):  # overload (strike, forward, maturity, params)
+            p = params if params is not None else alpha
+            alpha, rho, nu = p.alpha, p.rho, p.nu
+        self._check(strike, forward, maturity, alpha, rho, nu)
+        return float(self._vols([strike], forward, maturity, alpha, rho, nu)[0])
+
+    def atm_volatility(self, forward: float, maturity: float, alpha: float, rho: float, nu: float) -> float:
+        """sabr.cpp:95-128.  Evaluated as the K = F branch of implied_volatility (identical arithmetic for
+        maturity >= 1e-10; below that the T-correction is < 1e-10 relative and is dropped as in :152-155)."""
+        self._check(None, forward, maturity, alpha, rho, nu)
+        return float(self._vols([forward], forward, maturity, alpha, rho, nu)[0])
+
+    def implied_volatilities(self, strikes: Sequence[float], forward: float, maturity: float, alpha: float, rho: float,
+                             nu: float) -> List[float]:
+        for k in strikes:
+            self._check(k, forward, maturity, alpha, rho, nu)
+        if len(strikes) == 0:
+            return []
+        return [float(v) for v in self._vols(strikes, forward, maturity, alpha, rho, nu)]
+
+    def volatility_sensitivities(self, strike: float, forward: float, maturity: float, alpha: float, rho: float,
+                                 nu: float):
+        """(d sigma/d alpha, d sigma/d rho, d sigma/d nu): the reference's central differences, sabr.cpp:250-279."""
+        ea, er, en = alpha * 0.001, 0.001, max(nu * 0.001, 0.0001)
+        iv = lambda a, r, n: self.implied_volatility(strike, forward, maturity, a, r, n)  # noqa: E731
+        d_alpha = (iv(alpha + ea, rho, nu) - iv(alpha - ea, rho, nu)) / (2.0 * ea)
+        r_up, r_dn = min(rho + er, 0.999), max(rho - er, -0.999)
+        d_rho = (iv(alpha, r_up, nu) - iv(alpha, r_dn, nu)) / (r_up - r_dn)
+        d_nu = (iv(alpha, rho, nu + en) - iv(alpha, rho, max(nu - en, 0.0))) / (2.0 * en)  # :274-277
+        return d_alpha, d_rho, d_nu
+
+
+sabr = types.ModuleType(__name__ + ".sabr", "SABR volatility model (B200 drop-in).")
+sabr.SABRParameters = SABRParameters
+sabr.SABRModel = SABRModel

@@ -6,7 +6,9 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["heston_b200.cu"]
+# (source, extra flags): the SABR unit must not contract a*b+c into FMAs (see its header)
+SOURCES = ["heston_b200.cu", "sabr_b200.cu"]
+EXTRA = {"sabr_b200.cu": ["-fmad=false"]}
 HEADERS = ["kernels.cuh", "fft_smem.cuh", "heston_math.cuh", os.path.join("..", "..", "include", "heston_b200.h")]
 TARGET = os.path.join(HERE, "libheston_b200.so")
 NVCC_FLAGS = [
@@ -26,11 +28,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return TARGET
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", TARGET, *SOURCES]
     env = dict(os.environ)
     env.pop("CC", None)  # this image exports CC/CXX wrappers nvcc must not pick up
     env.pop("CXX", None)
-    subprocess.run(cmd, cwd=HERE, check=True, env=env)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc, *compile_flags, *EXTRA.get(src, []), *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, src]
+        subprocess.run(cmd, cwd=HERE, check=True, env=env)
+        objs.append(obj)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", TARGET, *objs], cwd=HERE,
+                   check=True, env=env)
     return TARGET
 
 

@@ -308,6 +308,10 @@ int run_host(hb_plan* pl, const double* h_params, int P, int what, double* h_out
 
 }  // namespace
 
+// shared with sabr_b200.cu (separate translation unit, compiled with -fmad=false)
+extern "C" int hb_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+extern "C" void hb_internal_count_launch(void) { g_launches++; }
+
 extern "C" {
 
 int hb_version(void) { return 100; }

@@ -224,7 +224,8 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
         if (V == 6) {
             // all six variants of a maturity resident: shared stages and twiddles (refgrid_job6_kernel);
             // small batches run one job per (set, maturity)
-            static int rc6 = set_smem(refgrid_job6_kernel, kRef6Smem);
+            // the attribute is per device: set it on every launch (a process may drive several GPUs)
+            int rc6 = set_smem(refgrid_job6_kernel, kRef6Smem);
             if (rc6) return rc6;
             const int max_ctas = pl->sm_count;
             const bool split = M > 0 && (long long)P < 2LL * max_ctas && smem_rows <= (size_t(1) << 30);
@@ -668,12 +669,12 @@ int hb_fft_batch(double* d_data, int n, int n_slices, void* stream) {
     constexpr int STAGES = 3;
     const size_t smem = fft_smem_bytes(n, STAGES);
     if (n == 4096) {
-        static int rc4096 = set_smem(fft_batch_kernel<4096, 512, STAGES>, fft_smem_bytes(4096, STAGES));
+        int rc4096 = set_smem(fft_batch_kernel<4096, 512, STAGES>, fft_smem_bytes(4096, STAGES));  // per device
         if (rc4096) return rc4096;
         fft_batch_kernel<4096, 512, STAGES><<<std::min(n_slices, sms), 512, smem, (cudaStream_t)stream>>>(
             (double2*)d_data, n_slices);
     } else {
-        static int rc512 = set_smem(fft_batch_kernel<512, 64, STAGES>, fft_smem_bytes(512, STAGES));
+        int rc512 = set_smem(fft_batch_kernel<512, 64, STAGES>, fft_smem_bytes(512, STAGES));  // per device
         if (rc512) return rc512;
         fft_batch_kernel<512, 64, STAGES><<<std::min(n_slices, 4 * sms), 64, smem, (cudaStream_t)stream>>>(
             (double2*)d_data, n_slices);

@@ -242,6 +242,12 @@ HB_HD double tail_ub(const TailPoint& t, double l1g, double T, double kts, doubl
     const double ub = kts * (fma_(t.nre, T, l1g) + c1) + v0s * t.cD - ui * lsm;
     return ((t.dre * T > 5.0) && (kts >= 0.0) && (v0s >= 0.0)) ? ub : HUGE_VAL;
 }
+// l1g without the logarithm: |g| <= 2 gives |1 - g| <= 3, so 2 log|1 - g| <= 2 log 3.  Looser by a few units of
+// kts at most (84 % instead of 89 % of the underflowed pairs), but free: used where stage A is not cached.
+HB_HD double tail_l1g_const(const StageA& a) {
+    const double g2 = a.g.re * a.g.re + a.g.im * a.g.im;
+    return (g2 <= 4.0) ? 2.1973 : HUGE_VAL;  // 2 log 3 = 2.19722..., rounded up
+}
 HB_HD bool tail_dead(const StageA& a, double l1g, double T, double kts, double v0s, double lsm, double ui) {
     return tail_ub(tail_point(a), l1g, T, kts, v0s, lsm, ui) < -750.0;
 }

@@ -555,6 +555,21 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         // Simpson weight times e^{i b v_j} = (-1)^j   
                         const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
                         a = stage_a_tab(cc, v, gc.ui, gc.alpha, wgt, &tab);
+                        // Long grids reach far into the decayed tail (N = 16384, eta = 0.25: 72 % of all
+                        // (point, maturity) pairs): the rigorous bound of heston_math.cuh, in its log-free
+                        // form, says from stage A alone where a slice is exactly 0.
+                        const TailPoint tp = tail_point(a);
+                        const double l1g = tail_l1g_const(a);
+                        unsigned bits = 0u;
+                        for (int g = 0; g < count; ++g) {
+                            const SubSlice& s = grp.s[g];
+                            bits |= (tail_ub(tp, l1g, s.T, s.kts, s.v0s, s.lsm, gc.ui) < -750.0 ? 1u : 0u) << g;
+                        }
+                        gone = (gone & ~(7u << (3 * k))) | (bits << (3 * k));
+                        if (bits == (1u << count) - 1u) {
+                            for (int g = 0; g < count; ++g) sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
+                            continue;
+                        }
                     } else {
                         tab = tab_n;
                     }
@@ -588,7 +603,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
 #pragma unroll 1
                     for (int g = 0; g < count; ++g) {
                         const SubSlice& s = grp.s[g];
-                        const bool g_gone = ONEVAR && ((gone >> (3 * k + g)) & 1u);  // this slice alone is exactly 0 here
+                        // this slice alone is exactly 0 here (never with a shared stage B: all or nothing there)
+                        const bool g_gone = (ONEVAR || DECIM) && !share_b && ((gone >> (3 * k + g)) & 1u);
                         if ((g == 0 || !share_b) && !g_gone) b = stage_b(a, s.T);
                         if (!DECIM && g == last_b && !(ONEVAR && ((skip >> kn) & 1u))) {
                             a = ac[kn];

@@ -167,6 +167,32 @@ struct StageB {
     cplx Dq;  // (xi-d) (1-e)/(1-g e)
 };
 
+// ---- asymptotic stage B -------------------------------------------------------------------------------
+// Once Re(d) T > 45, e = exp(-d T) is below 2.9e-20 in modulus and drops out of stage B in double
+// precision: 1 - e = 1, 1 - g e = 1 (to far less than an ulp; what is left of it moves the exponent of phi
+// by at most (4 kts + 3 v0s |num|) |e| < 1e-16 wherever phi has not underflowed), so
+//   B  = (xi - d) T - 2 log(1/(1 - g)) = (xi - d) T - L0,   L0 = 2 clog(1 + g/(1-g))   T-independent
+//   Dq = xi - d
+// L0 is formed once per (class, grid point) by the same clog1p routine stage_b uses, fed with e = 0, and
+// stage B costs two FMAs instead of a cexp and a clog.  On the Carr-Madan grid (N = 4096, eta = 0.25) 43 %
+// of all (point, maturity) pairs are in this regime, 40 % have underflowed altogether, and 17 % need the
+// full stage B.  The rule depends on the slice alone (its own d and T), so a slice still evaluates to the
+// same bits whichever group or launch path it is priced in.
+constexpr double kAsymDT = 45.0;
+
+HB_HD cplx stage_b_l0(const StageA& a) {
+    double lg, ar, rn;
+    clog1p_rcp_nb(a.q1.re, a.q1.im, 1.0, &lg, &ar, &rn);
+    return {lg, 2.0 * ar};
+}
+HB_HD StageB stage_b_asym(const StageA& a, cplx l0, double T) {
+    StageB b;
+    b.B.re = a.num.re * T - l0.re;
+    b.B.im = a.num.im * T - l0.im;
+    b.Dq = a.num;
+    return b;
+}
+
 HB_HD StageB stage_b(const StageA& a, double T) {
     StageB b;
     // e = exp(-d T)                                          heston.cpp:59

@@ -350,6 +350,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     StageA ac[PTS];
     cplx tabc[PTS];
     double l1gc[PTS];  // 2 log|1 - g| (decayed-tail bound of the one-variant modes, heston_math.cuh)
+    cplx l0c[PTS];     // L0 of the asymptotic stage B (heston_math.cuh), per (class, point) like stage A
     // deadm: one byte per maturity m, bit k: the base set's phi at this thread's k-th point and maturity m
     // has underflowed with a wide margin (see K1).  Only available when one CTA prices all classes of a set.
     // Indexed dynamically, once per group: lives in local memory, not in registers.
@@ -476,6 +477,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
                     ac[k] = stage_a_tab(cc, gc.eta * (double)j, gc.ui, gc.alpha, wgt, &tabc[k]);
                     if (ONEVAR) l1gc[k] = tail_l1g(ac[k]);
+                    l0c[k] = stage_b_l0(ac[k]);
                 }
                 cached_cls = cls;
             }
@@ -531,10 +533,11 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 // hides behind the remaining stage F (ncu r01_g: 3.3 % of all samples sat on the first use).
                 const int last_b = share_b ? 0 : count - 1;  // slice whose stage B is the last one of a point
                 StageA a = {};
-                cplx tab = {0.0, 0.0}, tab_n = {0.0, 0.0};
+                cplx tab = {0.0, 0.0}, tab_n = {0.0, 0.0}, l0 = {0.0, 0.0};
                 if (!DECIM) {
                     a = ac[0];
                     tab_n = tabc[0];
+                    l0 = l0c[0];
                 }
 #pragma unroll 1
                 for (int k = 0, j0 = tid; j0 < N; ++k, j0 += NT) {
@@ -548,6 +551,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         if (!DECIM && !((skip >> kn) & 1u)) {
                             a = ac[kn];
                             tab_n = tabc[kn];
+                            l0 = l0c[kn];
                         }
                         continue;
                     }
@@ -570,6 +574,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                             for (int g = 0; g < count; ++g) sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
                             continue;
                         }
+                        // L0 of the asymptotic stage B, only where some slice of the group will use it
+                        if (a.d.re * grp.s[count - 1].T > kAsymDT) l0 = stage_b_l0(a);
                     } else {
                         tab = tab_n;
                     }
@@ -577,10 +583,14 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     if (HB_F3 && share_b && count == 3) {
                         // {base, theta', v0'} of one maturity: one stage B, then the three final cexps in one
                         // interleaved evaluation (they underflow together: the sets differ by 1.5e-8 relative)
-                        b = stage_b(a, grp.s[0].T);
+                        {
+                            const double T0 = grp.s[0].T;
+                            b = (a.d.re * T0 > kAsymDT) ? stage_b_asym(a, l0, T0) : stage_b(a, T0);
+                        }
                         if (!DECIM) {
                             a = ac[kn];
                             tab_n = tabc[kn];
+                            l0 = l0c[kn];
                         }
                         double er[3], ei[3];
 #pragma unroll
@@ -605,10 +615,12 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         const SubSlice& s = grp.s[g];
                         // this slice alone is exactly 0 here (never with a shared stage B: all or nothing there)
                         const bool g_gone = (ONEVAR || DECIM) && !share_b && ((gone >> (3 * k + g)) & 1u);
-                        if ((g == 0 || !share_b) && !g_gone) b = stage_b(a, s.T);
+                        if ((g == 0 || !share_b) && !g_gone)
+                            b = (a.d.re * s.T > kAsymDT) ? stage_b_asym(a, l0, s.T) : stage_b(a, s.T);
                         if (!DECIM && g == last_b && !(ONEVAR && ((skip >> kn) & 1u))) {
                             a = ac[kn];
                             tab_n = tabc[kn];
+                            l0 = l0c[kn];
                         }
                         if (g_gone) {
                             sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});

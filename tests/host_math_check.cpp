@@ -59,3 +59,20 @@ extern "C" void hm_tail_bound(const double* p, int n, const double* ur, double u
         dead[j] = hb::tail_dead(a, hb::tail_l1g(a), T, s.kts, s.v0s, s.lsm, ui) ? 1 : 0;
     }
 }
+
+// asymptotic stage B next to the full one: exponent of phi from both, and Re(d) T
+extern "C" void hm_stage_b_asym(const double* p, int n, const double* ur, double ui, double T, double S0, double r,
+                                double q, double* er_full, double* ei_full, double* er_asym, double* ei_asym, double* dT) {
+    hb::ClassConst c = {p[0], p[2] * p[2], p[3] * p[2]};
+    hb::SliceConst s = {p[0] * p[1] / c.sigma2, p[4] / c.sigma2, log(S0) + (r - q) * T};
+    for (int j = 0; j < n; ++j) {
+        hb::StageA a = hb::stage_a(c, ur[j], ui);
+        hb::StageB bf = hb::stage_b(a, T), ba = hb::stage_b_asym(a, hb::stage_b_l0(a), T);
+        er_full[j] = s.kts * bf.B.re + s.v0s * bf.Dq.re - ui * s.lsm;
+        ei_full[j] = s.kts * bf.B.im + s.v0s * bf.Dq.im + ur[j] * s.lsm;
+        er_asym[j] = s.kts * ba.B.re + s.v0s * ba.Dq.re - ui * s.lsm;
+        ei_asym[j] = s.kts * ba.B.im + s.v0s * ba.Dq.im + ur[j] * s.lsm;
+        dT[j] = a.d.re * T;
+    }
+}
+

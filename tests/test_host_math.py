@@ -229,3 +229,33 @@ def test_tail_bound_is_rigorous_and_useful(hm):
                 n_caught += int(flagged.sum())
     assert n_dead > 0 and n_caught > 0.8 * n_dead, (n_caught, n_dead)
 
+
+def test_asymptotic_stage_b_is_the_full_one_beyond_dT_45(hm):
+    """heston_math.cuh stage_b_asym(): for Re(d) T > 45 the exponent of phi from the two-FMA form must equal the
+    one from the full stage B (cexp + clog) to rounding -- wherever phi has not underflowed, the difference has
+    to stay far below one ulp of exp (1.1e-16 relative in phi = 1.1e-16 absolute in the exponent)."""
+    from scipy.stats import qmc
+
+    corners = [np.where([(m >> b) & 1 for b in range(5)], UB, LB) for m in range(32)]
+    X = np.vstack([LB + (UB - LB) * qmc.Sobol(d=5, seed=13).random(128), corners])
+    v = 0.25 * np.arange(4096.0)
+    n_fast = n_alive = 0
+    worst = 0.0
+    for p in X:
+        p = np.ascontiguousarray(p, dtype=float)
+        for T in (0.1, 0.55, 1.0, 2.0):
+            o = [np.empty(v.size) for _ in range(5)]
+            hm.hm_stage_b_asym(_p(p), C.c_int(v.size), _p(v), C.c_double(-1.75), C.c_double(T), C.c_double(S0),
+                               C.c_double(R), C.c_double(Q), *[_p(x) for x in o])
+            er_f, ei_f, er_a, ei_a, dT = o
+            alive = er_f > -746.0
+            fast = (dT > 45.0) & alive
+            n_alive += int(alive.sum())
+            n_fast += int(fast.sum())
+            if fast.any():
+                # rounding of the two evaluations: a few ulp of the exponent's terms (|er| up to 746, kts up to 1e5)
+                scale = 1.0 + np.abs(er_f[fast]) + np.abs(ei_f[fast])
+                worst = max(worst, float(np.max(np.maximum(np.abs(er_a - er_f)[fast], np.abs(ei_a - ei_f)[fast]) / scale)))
+    assert n_fast > 0.5 * n_alive  # most of the live integrand is in the asymptotic regime
+    assert worst < 2e-15, worst
+

@@ -476,8 +476,12 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 for (int k = 0, j = tid; j < N; ++k, j += NT) {
                     const double wgt = gc.w0 * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
                     ac[k] = stage_a_tab(cc, gc.eta * (double)j, gc.ui, gc.alpha, wgt, &tabc[k]);
-                    if (ONEVAR) l1gc[k] = tail_l1g(ac[k]);
                     l0c[k] = stage_b_l0(ac[k]);
+                    // 2 log|1 - g| of the tail bound is -Re L0 (1 + g/(1-g) = 1/(1-g)); premise |g| <= 2 as in tail_l1g
+                    if (ONEVAR) {
+                        const double g2 = ac[k].g.re * ac[k].g.re + ac[k].g.im * ac[k].g.im;
+                        l1gc[k] = (g2 <= 4.0) ? -l0c[k].re : HUGE_VAL;
+                    }
                 }
                 cached_cls = cls;
             }

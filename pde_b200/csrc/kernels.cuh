@@ -649,7 +649,13 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             __syncthreads();
             if (N >= 4096) {
                 dif_pass<N, NT, (N >= 4096 ? N / 64 : 8), false>(slices, count, tw, tw512, grp.fmask, tid);
-                __syncthreads();
+                // The S = 8 butterfly of thread 8 blk' + t' reads the slots 64 blk' + t' + 8 r', written in the
+                // S = 64 pass by the threads 64 (blk' >> 3) + t' + 8 r': both sit in the same 64-thread group, so
+                // this hand-over needs a barrier among two warps only (named barriers 1..8), not the whole CTA.
+                if (N == 4096 && NT == 512)
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + (tid >> 6)) : "memory");
+                else
+                    __syncthreads();
             }
             K3Opt cur = k3_load(grp, 0);
             dif_pass<N, NT, 8, true>(slices, count, tw, tw512, grp.fmask, tid);  // only the digits the strikes need

@@ -665,11 +665,15 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             {
                 const int max_opt = grp.max_opt;
                 const int gg = (k3_g < count) ? k3_g : 0;
-                const SubSlice& s = grp.s[gg];
+                // copied out: after the early barrier below the descriptor buffer may be refilled for group gi + 2
+                const double s_disc = grp.s[gg].disc, s_fwd = grp.s[gg].fwd;
+                const int s_variant = grp.s[gg].variant;
                 const double2* sl = slices + (size_t)gg * N;
+                if (max_opt <= 0) __syncthreads();
                 for (int base = 0; base < max_opt; base += TPG / 2) {  // block-uniform trip count (shuffles inside)
+                    const bool last = base + TPG / 2 >= max_opt;
                     K3Opt nxt = cur;
-                    if (base + TPG / 2 < max_opt) nxt = k3_load(grp, base + TPG / 2);
+                    if (!last) nxt = k3_load(grp, base + TPG / 2);
                     double x = 0.0;
                     if (cur.bin >= 0) {
                         const int m = cur.bin + k3_half;
@@ -681,25 +685,28 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                             x = y.re * cs - y.im * sn;
                         }
                     }
+                    // The slices have been read for the last time: release them (and the 40 % of the CTA that has
+                    // no option to finish) to the next group's K1 before the interpolation and the global stores.
+                    if (last) __syncthreads();
                     const double x1 = __shfl_xor_sync(0xffffffffu, x, 1);
                     if (cur.o >= 0 && k3_half == 0) {
-                        double* dst = rows + (size_t)s.variant * n + cur.orig;
+                        double* dst = rows + (size_t)s_variant * n + cur.orig;
                         double price = __longlong_as_double(0x7ff8000000000000LL);
                         if (cur.bin >= 0) {
                             const double c0 = cur.s0 * x;
                             const double c1 = cur.s1 * x1;
-                            double call = s.disc * (c0 + (c1 - c0) * cur.frac);
+                            double call = s_disc * (c0 + (c1 - c0) * cur.frac);
                             if (ph > 0) call += *dst;
-                            price = (ph == R - 1) ? finish_price(call, cur.call != 0, s.fwd, cur.kdisc) : call;
+                            price = (ph == R - 1) ? finish_price(call, cur.call != 0, s_fwd, cur.kdisc) : call;
                         }
                         *dst = price;
                     }
                     cur = nxt;
                 }
             }
-            __syncthreads();  // slices are free again; the prefetched descriptor of group gi + 1 is visible
             }
         }
+        __syncthreads();  // the price rows of the last group are complete
         if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
     }
 }

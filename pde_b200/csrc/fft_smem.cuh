@@ -283,6 +283,13 @@ __device__ __forceinline__ int dif_pos(int m) {
 
 // X_m of a slice that went through every pass down to S = 8: the one needed output of its last
 // radix-8 butterfly (w8^k from the compact table behind W_512 and W_64).  WANT_IM = false returns Re X_m only (im = 0).
+// w8^k = e^{-2 pi i k/8} from the constant bank (f is the same for every lane of a warp in practice: the quoted
+// bins share their top digit, so the dynamic index is uniform)
+__constant__ double kW8c[8] = {1.0, 0.70710678118654752440, 0.0, -0.70710678118654752440,
+                               -1.0, -0.70710678118654752440, 0.0, 0.70710678118654752440};
+__constant__ double kW8s[8] = {0.0, -0.70710678118654752440, -1.0, -0.70710678118654752440,
+                               0.0, 0.70710678118654752440, 1.0, 0.70710678118654752440};
+
 template <int N, bool WANT_IM>
 __device__ __forceinline__ cplx dif_bin(const double2* sl, const double2* tw512, int m) {
     const int p = dif_pos<N>(m);
@@ -291,7 +298,7 @@ __device__ __forceinline__ cplx dif_bin(const double2* sl, const double2* tw512,
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const cplx v = lds_c(sl, p + r);
-        const double2 w = tw512[576 + ((r * f) & 7)];
+        const double2 w = make_double2(kW8c[(r * f) & 7], kW8s[(r * f) & 7]);
         acc.re = fma(v.re, w.x, fma(-v.im, w.y, acc.re));
         if (WANT_IM) acc.im = fma(v.re, w.y, fma(v.im, w.x, acc.im));
     }

@@ -35,7 +35,9 @@ struct cplx {
     double re, im;
 };
 
-HB_HD cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+// Explicit FMA placement: the contraction the compiler would pick may differ from one call site or template
+// instantiation to the next, and the launch paths are compared bit for bit.
+HB_HD cplx cmul(cplx a, cplx b) { return {fma_(a.re, b.re, -(a.im * b.im)), fma_(a.re, b.im, a.im * b.re)}; }
 
 // Parameter-set constants shared by every grid point of a (kappa,sigma,rho) class.
 struct ClassConst {
@@ -187,8 +189,8 @@ HB_HD cplx stage_b_l0(const StageA& a) {
 }
 HB_HD StageB stage_b_asym(const StageA& a, cplx l0, double T) {
     StageB b;
-    b.B.re = a.num.re * T - l0.re;
-    b.B.im = a.num.im * T - l0.im;
+    b.B.re = fma_(a.num.re, T, -l0.re);
+    b.B.im = fma_(a.num.im, T, -l0.im);
     b.Dq = a.num;
     return b;
 }
@@ -206,8 +208,8 @@ HB_HD StageB stage_b(const StageA& a, double T) {
     // lg = 2 Re log(ratio), ar = principal arg (as clog), rn = 1/|1 - g e|^2 -- evaluated together
     double lg, ar, rn;
     clog1p_rcp_nb(dl.re, dl.im, n.re * n.re + n.im * n.im, &lg, &ar, &rn);
-    b.B.re = a.num.re * T - lg;
-    b.B.im = a.num.im * T - 2.0 * ar;
+    b.B.re = fma_(a.num.re, T, -lg);
+    b.B.im = fma_(a.num.im, T, -(2.0 * ar));
     // Dq = num (1-e)/(1-g e)
     const cplx Q = cmul(ome, {n.re * rn, -n.im * rn});
     b.Dq = cmul(a.num, Q);

@@ -356,6 +356,15 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     // Indexed dynamically, once per group: lives in local memory, not in registers.
     constexpr int kDeadWords = 16;  // 128 maturities
     unsigned long long deadm[kDeadWords];
+// Rigorous tail bound in the cached (N = 4096) one-variant path: worth +13 % before the asymptotic stage B,
+// -4 % after it (a decayed point now costs two FMAs of stage B and the exponent): off.  The decimation path
+// keeps it (+8 % at N = 16384, eta = 0.25, where 72 % of the grid has decayed and stage A is not cached).
+#ifndef HB_BOUND
+#define HB_BOUND 0
+#endif
+#ifndef HB_BOUND_DECIM
+#define HB_BOUND_DECIM 1
+#endif
 #ifndef HB_F3
 #define HB_F3 1
 #endif
@@ -478,7 +487,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     ac[k] = stage_a_tab(cc, gc.eta * (double)j, gc.ui, gc.alpha, wgt, &tabc[k]);
                     l0c[k] = stage_b_l0(ac[k]);
                     // 2 log|1 - g| of the tail bound is -Re L0 (1 + g/(1-g) = 1/(1-g)); premise |g| <= 2 as in tail_l1g
-                    if (ONEVAR) {
+                    if (ONEVAR && HB_BOUND) {
                         const double g2 = ac[k].g.re * ac[k].g.re + ac[k].g.im * ac[k].g.im;
                         l1gc[k] = (g2 <= 4.0) ? -l0c[k].re : HUGE_VAL;
                     }
@@ -517,7 +526,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 // (For class 0 of the six-variant mode it was measured a loss: stage B is shared by three
                 // slices there, the bound costs more than it saves -- 17.7 vs 18.5 M slices/s.)
                 unsigned gone = 0u;
-                if (!DECIM && ONEVAR) {
+                if (!DECIM && ONEVAR && HB_BOUND) {
 #pragma unroll 2
                     for (int k = 0; k < PTS; ++k) {
                         const TailPoint tp = tail_point(ac[k]);
@@ -569,7 +578,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         const TailPoint tp = tail_point(a);
                         const double l1g = tail_l1g_const(a);
                         unsigned bits = 0u;
-                        for (int g = 0; g < count; ++g) {
+                        for (int g = 0; g < (HB_BOUND_DECIM ? count : 0); ++g) {
                             const SubSlice& s = grp.s[g];
                             bits |= (tail_ub(tp, l1g, s.T, s.kts, s.v0s, s.lsm, gc.ui) < -750.0 ? 1u : 0u) << g;
                         }

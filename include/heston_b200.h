@@ -23,6 +23,10 @@
  *     (std::invalid_argument -> ValueError, heston.cpp:28-35, :156-164).
  *   - There is no CPU fallback: without a CUDA device every compute call fails with
  *     HB_ERR_CUDA.
+ *   - Threading: a plan owns its workspace (price rows, job counter, staging buffers), so the calls on
+ *     ONE plan must be stream-ordered -- one stream at a time, or externally serialised; different plans
+ *     are independent and may be driven from different host threads and streams concurrently (the
+ *     reference's model objects are const and share nothing either, heston.hpp:117-258).
  */
 #ifndef HESTON_B200_H
 #define HESTON_B200_H

@@ -180,7 +180,10 @@ struct StageB {
 // of all (point, maturity) pairs are in this regime, 40 % have underflowed altogether, and 17 % need the
 // full stage B.  The rule depends on the slice alone (its own d and T), so a slice still evaluates to the
 // same bits whichever group or launch path it is priced in.
-constexpr double kAsymDT = 45.0;
+#ifndef HB_ASYM_DT
+#define HB_ASYM_DT 45.0
+#endif
+constexpr double kAsymDT = HB_ASYM_DT;
 
 HB_HD cplx stage_b_l0(const StageA& a) {
     double lg, ar, rn;

@@ -184,6 +184,7 @@ struct StageB {
 #define HB_ASYM_DT 45.0
 #endif
 constexpr double kAsymDT = HB_ASYM_DT;
+constexpr double kMidDT = 10.0;  // below this L0 need not exist (decimation path) and |g e| <= 2^-17 is rare anyway
 
 HB_HD cplx stage_b_l0(const StageA& a) {
     double lg, ar, rn;
@@ -198,11 +199,42 @@ HB_HD StageB stage_b_asym(const StageA& a, cplx l0, double T) {
     return b;
 }
 
-HB_HD StageB stage_b(const StageA& a, double T) {
+// Intermediate regime: with e = exp(-d T)
+// known and x = g e small (|x| <= 2^-17, i.e. Re(d) T above ~12.5), log(1 - x) and 1/(1 - x) have three-term
+// series whose truncation (|x|^4 / 4 < 1e-21) is far below rounding, so stage B needs the cexp but no clog
+// and no reciprocal:
+//   log(ratio) = log(1 + q1) + log(1 - x) = L0/2 - s,  s = x + x^2/2 + x^3/3   (argument wrapped to (-pi, pi])
+//   Dq = num (1 - e) (1 + x + x^2 + x^3)
+// tests/test_host_math.py compares it with the full stage B point by point.
+HB_HD bool stage_b_mid_ok(const StageA& a, cplx e) {
+    const double gr = a.g.re * e.re - a.g.im * e.im, gi = a.g.re * e.im + a.g.im * e.re;
+    return gr * gr + gi * gi <= 5.8e-11;  // |g e|^2 <= 2^-34
+}
+HB_HD StageB stage_b_mid(const StageA& a, cplx l0, cplx e, double T) {
     StageB b;
-    // e = exp(-d T)                                          heston.cpp:59
-    cplx e;
-    cexp_nb(-a.d.re * T, -a.d.im * T, &e.re, &e.im);
+    const cplx x = cmul(a.g, e);
+    cplx t = {fma_(x.re, 1.0 / 3.0, 0.5), x.im * (1.0 / 3.0)};
+    t = cmul(x, t);
+    t.re += 1.0;
+    const cplx s = cmul(x, t);  // -log(1 - x)
+    const double pi = 3.14159265358979323846;
+    double arg = fma_(0.5, l0.im, -s.im);  // principal value of the product's argument
+    arg = (arg > pi) ? arg - 2.0 * pi : ((arg <= -pi) ? arg + 2.0 * pi : arg);
+    b.B.re = fma_(a.num.re, T, -fma_(-2.0, s.re, l0.re));
+    b.B.im = fma_(a.num.im, T, -(2.0 * arg));
+    cplx u = {1.0 + x.re, x.im};
+    u = cmul(x, u);
+    u.re += 1.0;
+    u = cmul(x, u);
+    u.re += 1.0;  // 1 + x + x^2 + x^3
+    const cplx ome = {1.0 - e.re, -e.im};
+    b.Dq = cmul(a.num, cmul(ome, u));
+    return b;
+}
+
+// Stage B given e = exp(-d T): everything after the cexp of heston.cpp:59.
+HB_HD StageB stage_b_rest(const StageA& a, cplx e, double T) {
+    StageB b;
     const cplx ome = {1.0 - e.re, -e.im};  // 1 - e
     // ratio = (1-g e)/(1-g) = 1 + delta, delta = g (1-e)/(1-g)
     const cplx dl = cmul(a.q1, ome);
@@ -217,6 +249,26 @@ HB_HD StageB stage_b(const StageA& a, double T) {
     const cplx Q = cmul(ome, {n.re * rn, -n.im * rn});
     b.Dq = cmul(a.num, Q);
     return b;
+}
+
+HB_HD StageB stage_b(const StageA& a, double T) {
+    // e = exp(-d T)                                          heston.cpp:59
+    cplx e;
+    cexp_nb(-a.d.re * T, -a.d.im * T, &e.re, &e.im);
+    return stage_b_rest(a, e, T);
+}
+
+// Stage B by regime (the fused kernel's entry point): asymptotic beyond Re(d) T = 45, series form where
+// |g e| <= 2^-17, the full form otherwise.  The choice depends on the slice alone.
+#ifndef HB_MID
+#define HB_MID 1
+#endif
+HB_HD StageB stage_b_auto(const StageA& a, cplx l0, double T) {
+    if (a.d.re * T > kAsymDT) return stage_b_asym(a, l0, T);
+    cplx e;
+    cexp_nb(-a.d.re * T, -a.d.im * T, &e.re, &e.im);
+    if (HB_MID && a.d.re * T > kMidDT && stage_b_mid_ok(a, e)) return stage_b_mid(a, l0, e, T);
+    return stage_b_rest(a, e, T);
 }
 
 // Per-slice constants of stage F.

@@ -587,8 +587,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                             for (int g = 0; g < count; ++g) sts_c(slices + (size_t)g * N, j0, {0.0, 0.0});
                             continue;
                         }
-                        // L0 of the asymptotic stage B, only where some slice of the group will use it
-                        if (a.d.re * grp.s[count - 1].T > kAsymDT) l0 = stage_b_l0(a);
+                        // L0 of the asymptotic / series stage B, only where some slice of the group can use it
+                        if (a.d.re * grp.s[count - 1].T > kMidDT) l0 = stage_b_l0(a);
                     } else {
                         tab = tab_n;
                     }
@@ -598,7 +598,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         // interleaved evaluation (they underflow together: the sets differ by 1.5e-8 relative)
                         {
                             const double T0 = grp.s[0].T;
-                            b = (a.d.re * T0 > kAsymDT) ? stage_b_asym(a, l0, T0) : stage_b(a, T0);
+                            b = stage_b_auto(a, l0, T0);
                         }
                         if (!DECIM) {
                             a = ac[kn];
@@ -629,7 +629,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         // this slice alone is exactly 0 here (never with a shared stage B: all or nothing there)
                         const bool g_gone = (ONEVAR || DECIM) && !share_b && ((gone >> (3 * k + g)) & 1u);
                         if ((g == 0 || !share_b) && !g_gone)
-                            b = (a.d.re * s.T > kAsymDT) ? stage_b_asym(a, l0, s.T) : stage_b(a, s.T);
+                            b = stage_b_auto(a, l0, s.T);
                         if (!DECIM && g == last_b && !(ONEVAR && ((skip >> kn) & 1u))) {
                             a = ac[kn];
                             tab_n = tabc[kn];

@@ -76,3 +76,21 @@ extern "C" void hm_stage_b_asym(const double* p, int n, const double* ur, double
     }
 }
 
+// intermediate-regime stage B next to the full one (flag = 1 where stage_b_mid_ok holds)
+extern "C" void hm_stage_b_mid(const double* p, int n, const double* ur, double ui, double T, double S0, double r,
+                               double q, double* er_full, double* ei_full, double* er_mid, double* ei_mid, int* flag) {
+    hb::ClassConst c = {p[0], p[2] * p[2], p[3] * p[2]};
+    hb::SliceConst s = {p[0] * p[1] / c.sigma2, p[4] / c.sigma2, log(S0) + (r - q) * T};
+    for (int j = 0; j < n; ++j) {
+        hb::StageA a = hb::stage_a(c, ur[j], ui);
+        hb::cplx e;
+        hb::cexp_nb(-a.d.re * T, -a.d.im * T, &e.re, &e.im);
+        hb::StageB bf = hb::stage_b(a, T), bm = hb::stage_b_mid(a, hb::stage_b_l0(a), e, T);
+        er_full[j] = s.kts * bf.B.re + s.v0s * bf.Dq.re - ui * s.lsm;
+        ei_full[j] = s.kts * bf.B.im + s.v0s * bf.Dq.im + ur[j] * s.lsm;
+        er_mid[j] = s.kts * bm.B.re + s.v0s * bm.Dq.re - ui * s.lsm;
+        ei_mid[j] = s.kts * bm.B.im + s.v0s * bm.Dq.im + ur[j] * s.lsm;
+        flag[j] = hb::stage_b_mid_ok(a, e) ? 1 : 0;
+    }
+}
+

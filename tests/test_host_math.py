@@ -259,3 +259,31 @@ def test_asymptotic_stage_b_is_the_full_one_beyond_dT_45(hm):
     assert n_fast > 0.5 * n_alive  # most of the live integrand is in the asymptotic regime
     assert worst < 2e-15, worst
 
+
+def test_intermediate_stage_b_matches_the_full_one(hm):
+    """heston_math.cuh stage_b_mid() (series for log(1 - g e) and 1/(1 - g e); prepared for the next round, not yet
+    called by the kernels): wherever its premise |g e| <= 2^-17 holds and phi has not underflowed, the exponent of
+    phi must equal the one from the full stage B to rounding."""
+    from scipy.stats import qmc
+
+    corners = [np.where([(m >> b) & 1 for b in range(5)], UB, LB) for m in range(32)]
+    X = np.vstack([LB + (UB - LB) * qmc.Sobol(d=5, seed=17).random(128), corners])
+    v = 0.25 * np.arange(4096.0)
+    n_mid = 0
+    worst = 0.0
+    for p in X:
+        p = np.ascontiguousarray(p, dtype=float)
+        for T in (0.1, 0.55, 1.0, 2.0):
+            o = [np.empty(v.size) for _ in range(4)]
+            flag = np.zeros(v.size, dtype=np.int32)
+            hm.hm_stage_b_mid(_p(p), C.c_int(v.size), _p(v), C.c_double(-1.75), C.c_double(T), C.c_double(S0),
+                              C.c_double(R), C.c_double(Q), *[_p(x) for x in o], flag.ctypes.data_as(C.POINTER(C.c_int)))
+            er_f, ei_f, er_m, ei_m = o
+            use = flag.astype(bool) & (er_f > -746.0)
+            n_mid += int(use.sum())
+            if use.any():
+                scale = 1.0 + np.abs(er_f[use]) + np.abs(ei_f[use])
+                worst = max(worst, float(np.max(np.maximum(np.abs(er_m - er_f)[use], np.abs(ei_m - ei_f)[use]) / scale)))
+    assert n_mid > 100000
+    assert worst < 2e-15, worst
+

@@ -263,11 +263,11 @@ HB_HD StageB stage_b(const StageA& a, double T) {
 #ifndef HB_MID
 #define HB_MID 1
 #endif
-HB_HD StageB stage_b_auto(const StageA& a, cplx l0, double T) {
+HB_HD StageB stage_b_auto(const StageA& a, cplx l0, double T, bool allow_mid = true) {
     if (a.d.re * T > kAsymDT) return stage_b_asym(a, l0, T);
     cplx e;
     cexp_nb(-a.d.re * T, -a.d.im * T, &e.re, &e.im);
-    if (HB_MID && a.d.re * T > kMidDT && stage_b_mid_ok(a, e)) return stage_b_mid(a, l0, e, T);
+    if (HB_MID && allow_mid && a.d.re * T > kMidDT && stage_b_mid_ok(a, e)) return stage_b_mid(a, l0, e, T);
     return stage_b_rest(a, e, T);
 }
 

@@ -588,7 +588,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                             continue;
                         }
                         // L0 of the asymptotic / series stage B, only where some slice of the group can use it
-                        if (a.d.re * grp.s[count - 1].T > kMidDT) l0 = stage_b_l0(a);
+                        // (the series form is not used here: without the cache its L0 would cost a clog per point and group)
+                        if (a.d.re * grp.s[count - 1].T > kAsymDT) l0 = stage_b_l0(a);
                     } else {
                         tab = tab_n;
                     }
@@ -598,7 +599,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         // interleaved evaluation (they underflow together: the sets differ by 1.5e-8 relative)
                         {
                             const double T0 = grp.s[0].T;
-                            b = stage_b_auto(a, l0, T0);
+                            b = stage_b_auto(a, l0, T0, !DECIM);
                         }
                         if (!DECIM) {
                             a = ac[kn];
@@ -629,7 +630,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         // this slice alone is exactly 0 here (never with a shared stage B: all or nothing there)
                         const bool g_gone = (ONEVAR || DECIM) && !share_b && ((gone >> (3 * k + g)) & 1u);
                         if ((g == 0 || !share_b) && !g_gone)
-                            b = stage_b_auto(a, l0, s.T);
+                            b = stage_b_auto(a, l0, s.T, !DECIM);
                         if (!DECIM && g == last_b && !(ONEVAR && ((skip >> kn) & 1u))) {
                             a = ac[kn];
                             tab_n = tabc[kn];

@@ -59,6 +59,20 @@ def sobol_sets(P, skip=0):
     return LB + (UB - LB) * s.random(P)
 
 
+def slow_decay_sets(P, skip=0):
+    """A population where nothing can be elided: sigma near 2, rho near -0.99, small kappa theta (SURVEY.md
+    App. D "no decay": |phi| is still O(1e3) at the end of the grid), so every grid point of every slice runs the
+    full stage B and F."""
+    from scipy.stats import qmc
+
+    lo = np.array([0.1, 0.01, 1.5, -0.99, 0.01])
+    hi = np.array([0.5, 0.05, 2.0, -0.90, 0.05])
+    s = qmc.Sobol(d=5, seed=11)
+    if skip:
+        s.fast_forward(skip)
+    return lo + (hi - lo) * s.random(P)
+
+
 def fd_variants(X):
     """Base + 5 forward-difference perturbed sets per row (SciPy 2-point rule with bounds)."""
     rstep = 1.4901161193847656e-08

@@ -84,6 +84,17 @@ int hb_surface_set(hb_plan* plan, int n_opt, const double* strike, const double*
  * heston_calibrator.py:465-477).  Default: the calibrator's DEFAULT_BOUNDS (:201-207). */
 int hb_set_bounds(hb_plan* plan, const double* lb5, const double* ub5);
 
+/* Significance cut of the Carr-Madan (FFT) modes.  The damped integrand decays exponentially in v; a grid
+ * point whose |phi| lies below e^cut is treated as exactly 0 (as the reference's own double arithmetic does
+ * once exp underflows, cut = -746).  cut is chosen per surface so that ALL dropped points together cannot move
+ * any price by more than `abs_price_error`:  e^cut * sum_j |w_j / denominator_j| * max_options(e^{-rT}
+ * e^{-alpha k}/pi) = abs_price_error.  Default 2^-80 (8.3e-25, twelve orders below the 1e-12 absolute parity
+ * tolerance); 0 = exact mode (only true underflow is skipped); values above 1e-12 are rejected.  REFGRID mode
+ * restates the reference's arithmetic and ignores it.  hb_plan_log_cut returns the cut in force (after
+ * hb_surface_set). */
+int hb_plan_set_truncation(hb_plan* plan, double abs_price_error);
+double hb_plan_log_cut(const hb_plan* plan);
+
 int hb_plan_n_options(const hb_plan* plan);
 int hb_plan_n_maturities(const hb_plan* plan); /* distinct maturities > 0 = slices per parameter set */
 

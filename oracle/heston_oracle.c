@@ -14,12 +14,18 @@
  *     tests/test_oracle.py) and against tests/golden/*.npz generated from
  *     that library and from the reference's Python calibrator.
  *   - ORC_MODE_FFT (Carr-Madan N-point FFT + log-strike interpolation):
- *     PARITY UNPINNED for the transform/interpolation stage.  The reference
- *     has no FFT pricer; the spec followed is
+ *     the reference has no FFT pricer, so no reference output
+ *     exists for the transform/interpolation stage.  The spec followed is
  *     docs/models/heston-model.md:89-106 (N, eta, order of steps) plus
  *     Carr & Madan (1999) Simpson-weighted FFT, with psi, alpha, scaling and
  *     clamp/parity taken from src/cpp/models/heston.cpp:109-149.  Its CF
- *     stage is the pinned orc_cf.
+ *     stage is the pinned orc_cf; the stage after it is PINNED TO AN
+ *     INDEPENDENT EVALUATION OF THAT SPEC: tests/golden/fft_direct.npz holds
+ *     105 prices formed from the compiled reference's own CF values by plain
+ *     O(N) direct sums at the two bracketing bins in 50-digit arithmetic
+ *     (tests/golden/make_golden_fft_direct.py -- no FFT, no code shared with
+ *     this file; N = 512 / 4096 / 16384); this restatement agrees with them
+ *     to 0.09 x (1e-12 relative + 1e-14 absolute), tests/test_oracle.py.
  *
  * All citations are file:line in /root/reference.
  * Complex arithmetic is C99 <complex.h>; gcc lowers double complex * and /

@@ -45,7 +45,8 @@ def build(ref: bool = True, pyref: bool = False) -> None:
 
 
 class Oracle:
-    """C restatement (port).  FFT mode is 'parity unpinned' (see heston_oracle.c)."""
+    """C restatement (port).  FFT mode: CF pinned to the compiled reference, transform / interpolation pinned
+    to the independent direct-sum golden tests/golden/fft_direct.npz (see heston_oracle.c)."""
 
     def __init__(self, path: str | None = None):
         path = path or os.path.join(HERE, "liborc.so")

@@ -31,6 +31,8 @@ SIGNATURES = {
     "hb_plan_destroy": (C.c_int, [_vp]),
     "hb_surface_set": (C.c_int, [_vp, C.c_int, _dp, _dp, _u8p, _dp, C.c_double, C.c_double, C.c_double]),
     "hb_set_bounds": (C.c_int, [_vp, _dp, _dp]),
+    "hb_plan_set_truncation": (C.c_int, [_vp, C.c_double]),
+    "hb_plan_log_cut": (C.c_double, [_vp]),
     "hb_plan_n_options": (C.c_int, [_vp]),
     "hb_plan_n_maturities": (C.c_int, [_vp]),
     "hb_price": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
@@ -70,10 +72,10 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.environ.get("PDE_B200_LIB"):
         from .csrc.build import build
 
-        build()
+        build()  # no-op when the library is newer than every source and header
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch

@@ -46,12 +46,25 @@ __device__ __forceinline__ void sts_c(double2* s, int i, cplx v) { s[swz(i)] = m
 
 // 8-point forward DFT in registers.  On return v[] holds X in bit-reversed order:
 // X0=v0 X1=v4 X2=v2 X3=v6 X4=v1 X5=v5 X6=v3 X7=v7.
+__device__ __forceinline__ void dft8_tail(cplx (&v)[8]);
 __device__ __forceinline__ void dft8(cplx (&v)[8]) {
-    const double s = 0.70710678118654752440;
     HB_BF(v[0], v[4]);
     HB_BF(v[1], v[5]);
     HB_BF(v[2], v[6]);
     HB_BF(v[3], v[7]);
+    dft8_tail(v);
+}
+// The same transform when v[4..7] are known zeros (decayed tail of the integrand): the first butterfly
+// stage degenerates to copies.  Same operations on the same values as dft8 -> identical bits.
+__device__ __forceinline__ void dft8_lo4(cplx (&v)[8]) {
+    v[4] = v[0];
+    v[5] = v[1];
+    v[6] = v[2];
+    v[7] = v[3];
+    dft8_tail(v);
+}
+__device__ __forceinline__ void dft8_tail(cplx (&v)[8]) {
+    const double s = 0.70710678118654752440;
     {  // v5 *= (1-i)/sqrt2 ; v6 *= -i ; v7 *= (-1-i)/sqrt2
         cplx t = v[5];
         v[5] = {(t.re + t.im) * s, (t.im - t.re) * s};
@@ -182,6 +195,8 @@ __device__ __forceinline__ void fft_pass(double2* base, int count, int gmax, con
 // from the FP64 pipe (the binding one) to the idle LSU.
 // ================================================================================================
 
+constexpr int kMaxGroupFft = 3;  // slices resident at once (kernels.cuh: kMaxGroup)
+
 template <int N>
 struct Log8 {
     static constexpr int value = 1 + Log8<N / 8>::value;
@@ -264,6 +279,92 @@ __device__ __forceinline__ void dif_pass(double2* base, int count, const double2
                     if (!MASKED || ((keep >> f) & 1u)) sts_c(sl, p0 + f * S, v[bitrev3(f)]);
             }
         }
+    }
+}
+
+// ---- zero-aware first two passes (N / 8 == NT: butterfly `tid` of the first pass owns exactly the points
+// tid + r N/8 that thread `tid` produced in K1) -------------------------------------------------------------
+// The integrand decays: beyond some index every point of a slice is an exact zero (exp underflow, or the plan's
+// significance cut).  K1 hands over what it knows -- bit 8 g + k of `live`: this thread's k-th point of slice g is
+// non-zero -- and the first pass skips what is trivially zero:
+//   no live point      nothing to do (the slots already hold K1's zeros)
+//   only row 0 live    X_f = v0 for every f: seven twiddle products, no butterfly
+//   rows 0..3 live     dft8_lo4
+// Results are bit-identical to transforming the stored zeros.
+template <int N, int NT>
+__device__ __forceinline__ void dif_pass_first(double2* base, int count, const double2* tw, unsigned live, int tid) {
+    static_assert(N / 8 == NT && N > 512, "first pass on the thread's own points, running twiddle powers");
+    constexpr int S = N / 8;
+    if (live == 0u) return;
+    cplx wf[8];
+    {
+        const double2 w = tw[tid];
+        wf[1] = {w.x, w.y};
+#pragma unroll
+        for (int f = 2; f < 8; ++f) wf[f] = cmul(wf[f - 1], wf[1]);
+    }
+#pragma unroll 1
+    for (int g = 0; g < count; ++g) {
+        const unsigned lm = (live >> (8 * g)) & 0xffu;
+        if (lm == 0u) continue;
+        double2* sl = base + (size_t)g * N;
+        if (lm == 1u) {
+            const cplx v0 = lds_c(sl, tid);
+#pragma unroll
+            for (int f = 1; f < 8; ++f) sts_c(sl, tid + f * S, cmul(v0, wf[f]));
+            continue;
+        }
+        cplx v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = ((lm >> r) != 0u) ? lds_c(sl, tid + r * S) : cplx{0.0, 0.0};
+        if (lm < 16u) dft8_lo4(v);
+        else dft8(v);
+#pragma unroll
+        for (int f = 1; f < 8; ++f) v[bitrev3(f)] = cmul(v[bitrev3(f)], wf[f]);
+#pragma unroll
+        for (int f = 0; f < 8; ++f) sts_c(sl, tid + f * S, v[bitrev3(f)]);
+    }
+}
+
+// Second pass (S = N/64).  jlive[g] = 1 + the highest non-zero point index of slice g (0: none).  If it is at
+// most N/8 only row 0 of the first pass was live, every sub-slice f holds y_f[t] = x_t W^{t f} with support
+// t < jlive, and the butterfly of thread (c, t) reads the elements t + r S of sub-slice c: rows with
+// t + r S >= jlive are zeros and are neither loaded nor added.
+template <int N, int NT>
+__device__ __forceinline__ void dif_pass_second(double2* base, int count, const double2* tw512, const int* jlive,
+                                                int tid) {
+    static_assert(N / 8 == NT && N == 4096, "stride N/64 = 64, W_512 twiddles");
+    constexpr int S = N / 64;
+    const int t = tid & (S - 1);
+    const int p0 = ((tid - t) << 3) + t;
+    int nr[kMaxGroupFft];
+    int any = 0;
+#pragma unroll
+    for (int g = 0; g < kMaxGroupFft; ++g) {
+        const int J = (g < count) ? jlive[g] : 0;
+        nr[g] = (J > N / 8) ? 8 : max(0, min(8, (J - t + S - 1) / S));
+        any |= nr[g];
+    }
+    if (any == 0) return;
+    cplx wf[8];
+#pragma unroll
+    for (int f = 1; f < 8; ++f) {
+        const double2 w = tw512[(t * f) & 511];
+        wf[f] = {w.x, w.y};
+    }
+#pragma unroll
+    for (int g = 0; g < kMaxGroupFft; ++g) {
+        if (g >= count || nr[g] == 0) continue;
+        double2* sl = base + (size_t)g * N;
+        cplx v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = (r < nr[g]) ? lds_c(sl, p0 + r * S) : cplx{0.0, 0.0};
+        if (nr[g] <= 4) dft8_lo4(v);
+        else dft8(v);
+#pragma unroll
+        for (int f = 1; f < 8; ++f) v[bitrev3(f)] = cmul(v[bitrev3(f)], wf[f]);
+#pragma unroll
+        for (int f = 0; f < 8; ++f) sts_c(sl, p0 + f * S, v[bitrev3(f)]);
     }
 }
 

@@ -98,6 +98,11 @@ struct hb_plan {
     hb_plan* sib[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool sib_stale = true;
     Arena gk;
+    // significance cut of the Carr-Madan modes (hb_plan_set_truncation; GridConst::cut)
+    double trunc_abs = 8.271806125530277e-25;  // 2^-80 absolute price units
+    double w_sum = 0.0;                        // sum_j |tab_j| over the damped grid
+    double scale_max = 0.0;                    // max over the surface of disc * e^{-alpha k_m}/pi
+    bool tail_ok = true;                       // FD bounds inside the validated default box
     const double* d_strike = nullptr;    // caller-order copies for the implied-vol epilogue
     const double* d_maturity = nullptr;
     const uint8_t* d_is_call = nullptr;
@@ -158,7 +163,11 @@ int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, do
     if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
     const SurfaceDev& S = pl->S;
     const int n = S.n_opt, M = S.n_mat, V = (what >= W_NEQ) ? 6 : 1;
-    GridConst gc = {pl->eta, pl->alpha, -(pl->alpha + 1.0), pl->eta / 3.0, pl->R, pl->N};
+    GridConst gc = {pl->eta, pl->alpha, -(pl->alpha + 1.0), pl->eta / 3.0, pl->R, pl->N, kUnderflow, kUnderflow - 54.0,
+                    pl->tail_ok ? 1 : 0};
+    // all dropped points together move a price by less than e^cut * w_sum * scale_max = trunc_abs
+    gc.cut = hb_plan_log_cut(pl);
+    gc.cut_dead = gc.cut - 54.0;
     const size_t row_bytes = (size_t)6 * std::max(n, 1) * sizeof(double);
     // dynamic job queue: one counter per plan, reset in stream order before each launch
     {
@@ -363,6 +372,13 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     std::memcpy(pl->bd.lb, lb, sizeof lb);
     std::memcpy(pl->bd.ub, ub, sizeof ub);
     if (mode == HB_MODE_FFT) {
+        // sum_j |w_j / (alpha^2 + alpha - v_j^2 + i (2 alpha + 1) v_j)|: what a unit-modulus phi would put on the grid
+        double ws = 0.0;
+        for (int j = 0; j < n_grid; ++j) {
+            const double v = eta * (double)j, a = alpha * alpha + alpha - v * v, b = (2.0 * alpha + 1.0) * v;
+            ws += (eta / 3.0) * (j == 0 ? 1.0 : ((j & 1) ? 4.0 : 2.0)) / std::sqrt(a * a + b * b);
+        }
+        pl->w_sum = ws;
         int rc = HB_OK;
         if (n_grid > 4096) {
             rc = set_smem(fft_job_kernel<4096, kNT4096, true, true>, job_smem_bytes(4096, gmax_for(4096)));
@@ -410,7 +426,29 @@ int hb_set_bounds(hb_plan* pl, const double* lb5, const double* ub5) {
         if (!(lb5[c] <= ub5[c])) return fail(HB_ERR_INVALID_ARGUMENT, "need lb <= ub");
     std::memcpy(pl->bd.lb, lb5, 5 * sizeof(double));
     std::memcpy(pl->bd.ub, ub5, 5 * sizeof(double));
+    // The perturbed-class tail skip (kernels.cuh, track_tail) rests on a condition number measured over the
+    // calibrator's default box (tests/test_host_math.py::test_tail_skip_margin): outside it the skip is off.
+    const double dlb[5] = {0.1, 0.01, 0.01, -0.99, 0.01}, dub[5] = {10.0, 1.0, 2.0, 0.99, 1.0};
+    pl->tail_ok = true;
+    for (int c = 0; c < 5; ++c) pl->tail_ok = pl->tail_ok && lb5[c] >= dlb[c] && ub5[c] <= dub[c];
     return HB_OK;
+}
+
+int hb_plan_set_truncation(hb_plan* pl, double abs_price_error) {
+    if (!pl) return fail(HB_ERR_INVALID_ARGUMENT, "plan is NULL");
+    if (!(abs_price_error >= 0.0) || !(abs_price_error <= 1e-12))
+        return fail(HB_ERR_INVALID_ARGUMENT, "truncation error must lie in [0, 1e-12] (0 = exact)");
+    pl->trunc_abs = abs_price_error;
+    for (hb_plan* sp : pl->sib)
+        if (sp) sp->trunc_abs = abs_price_error;
+    return HB_OK;
+}
+
+double hb_plan_log_cut(const hb_plan* pl) {
+    if (!pl || pl->mode != HB_MODE_FFT || !(pl->trunc_abs > 0.0) || !(pl->w_sum > 0.0) || !(pl->scale_max > 0.0))
+        return kUnderflow;
+    const double cut = std::log(pl->trunc_abs / (pl->w_sum * pl->scale_max));
+    return cut == cut ? std::min(-36.0, std::max(kUnderflow, cut)) : kUnderflow;
 }
 
 int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* maturity, const uint8_t* is_call,
@@ -461,6 +499,7 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     std::vector<double> opt_frac, opt_s0, opt_s1, opt_lnk, opt_kdisc;
     std::vector<uint8_t> opt_call;
     const int Nsub = pl->Nsub;
+    double scale_max = 0.0;
     for (int m = 0; m < M; ++m) {
         const double T = mats[m];
         const double disc = std::exp(-rate * T);  // heston.cpp:106
@@ -487,6 +526,7 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                     opt_frac.push_back((k - km) / lambda);
                     opt_s0.push_back(std::exp(-alpha * km) / kPi);
                     opt_s1.push_back(std::exp(-alpha * km1) / kPi);
+                    scale_max = std::max(scale_max, disc * std::max(opt_s0.back(), opt_s1.back()));
                     // digit of the on-chip transform's output index that the S = 8 pass resolves
                     for (int h = 0; h < 2; ++h) {
                         const int ms = (mm + h) % Nsub;
@@ -552,6 +592,7 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     pl->h_strike.assign(strike, strike + n_opt);
     pl->h_maturity.assign(maturity, maturity + n_opt);
     pl->h_call.assign(is_call, is_call + n_opt);
+    pl->scale_max = scale_max;
     pl->sib_stale = true;
     pl->has_surface = true;
     pl->has_market = market != nullptr;
@@ -607,6 +648,7 @@ int hb_greeks(hb_plan* pl, const double* d_params, int ld, int P, double* d_gree
         for (int i = 0; i < 5; ++i) {
             int rc;
             if (!pl->sib[i] && (rc = hb_plan_create(pl->mode, pl->N, pl->eta, pl->alpha, pl->device, &pl->sib[i]))) return rc;
+            pl->sib[i]->trunc_abs = pl->trunc_abs;
             const double* T = (i == 4) ? Tm.data() : pl->h_maturity.data();
             if ((rc = hb_surface_set(pl->sib[i], n, pl->h_strike.data(), T, pl->h_call.data(), nullptr, spot[i],
                                      rate[i], q)))

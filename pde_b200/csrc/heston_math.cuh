@@ -279,7 +279,12 @@ struct SliceConst {
 };
 
 // phi = exp(C + D v0 + i u (ln S0 + (r-q)T)),  i u = (-ui, ur)        heston.cpp:87-91
-HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui, double* er_out = nullptr) {
+// Below kUnderflow exp gives exactly 0 in double precision.  `cut` >= kUnderflow is the significance cut of the
+// Carr-Madan modes (kernels.cuh, GridConst::cut): |phi| = e^er < e^cut contributes less than the plan's
+// admissible absolute price error even if every grid point sat at the cut, and is treated as 0 as well.
+constexpr double kUnderflow = -746.0;
+HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui, double* er_out = nullptr,
+                   double cut = kUnderflow) {
     // explicit FMA order: the fused kernel restates these two lines inline (cexp_w<3> path) and must round alike
     const double er = fma_(s.kts, b.B.re, fma_(s.v0s, b.Dq.re, -(ui * s.lsm)));
     const double ei = fma_(s.kts, b.B.im, fma_(s.v0s, b.Dq.im, ur * s.lsm));
@@ -288,7 +293,7 @@ HB_HD cplx stage_f(const StageB& b, const SliceConst& s, double ur, double ui, d
     // cexp is skipped -- bit-identical output (sign of zero aside).  On the calibrator's box ~40 % of the
     // grid points of a slice are in this regime (the integrand has decayed); consecutive lanes hold
     // consecutive grid points, so whole warps take the short path.  NaN compares false and falls through.
-    if (er < -746.0) return {0.0, 0.0};
+    if (er < cut) return {0.0, 0.0};
     cplx phi;
     cexp_nb(er, ei, &phi.re, &phi.im);
     return phi;

@@ -64,13 +64,20 @@ struct GridConst {
     //   X[m] = sum_ph W_N^{ph m} Y_ph[m mod Nsub]
     // is accumulated only at the quoted bins.  R = 1 is the plain single-transform path.
     int R, n_full;
+    // Significance cut (hb_plan_set_truncation): a grid point with log|phi| < cut is treated as exactly 0.
+    // |x_j| = |phi_j| |tab_j| < e^cut |tab_j|, so all dropped points together move X_m by less than
+    // e^cut sum_j |tab_j| and a price by less than that times max_o(scale_o) -- the host picks cut so that this
+    // bound equals the plan's admissible absolute price error (default 2^-80; 0 = exact: cut = -746, where exp
+    // underflows).  cut_dead = cut - 54: margin below which the perturbed classes trust the base set's decay.
+    double cut, cut_dead;
+    int tail_ok;  // FD bounds inside the box the perturbed-class tail skip was validated on
 };
 
 struct Bounds {
     double lb[5], ub[5];
 };
 
-constexpr int kMaxGroup = 3;
+constexpr int kMaxGroup = kMaxGroupFft;
 
 struct SubSlice {
     double T, kts, v0s, lsm, disc, fwd;
@@ -327,6 +334,12 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     double2* slices = reinterpret_cast<double2*>(smem_raw);
     double2* tw = slices + (size_t)gmax * N;
     double2* tw512 = tw + N / 8;
+#ifndef HB_ZERO_AWARE
+#define HB_ZERO_AWARE 1
+#endif
+    // zero-aware first two transform passes (fft_smem.cuh): only where butterfly `tid` owns thread `tid`'s points
+    constexpr bool kZeroAware = HB_ZERO_AWARE && N == 4096 && N / 8 == NT;
+    __shared__ int s_jlive[2][kMaxGroup];  // [group parity][slice]: 1 + highest non-zero point index
     __shared__ Group grps[2];  // descriptor of the running group and, prefetched during its K1, of the next one
     __shared__ JobState js;
     __shared__ double red[(NT / 32) * 23];
@@ -371,7 +384,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
 #ifndef HB_TAIL
 #define HB_TAIL 1
 #endif
-    const bool track_tail = HB_TAIL && !DECIM && !split && V > 1 && M <= 8 * kDeadWords;
+    const bool track_tail = HB_TAIL && gc.tail_ok && !DECIM && !split && V > 1 && M <= 8 * kDeadWords;
 
     // Jobs differ in cost (decayed tails take the short path of stage F), so after its first,
     // statically assigned job a CTA pulls the next one from a global counter.
@@ -436,6 +449,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
         }
         __syncthreads();  // previous job's finalize has consumed rows/js
         if (tid == 0) {
+#pragma unroll
+            for (int g = 0; g < kMaxGroup; ++g) s_jlive[0][g] = s_jlive[1][g] = 0;
             job_setup(js, params, ld, p, bd, V);
             if (js.valid) {
                 int cls, n_total, t0;
@@ -495,6 +510,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 cached_cls = cls;
             }
             for (int ph = 0; ph < R; ++ph) {
+            unsigned live = 0u;  // bit 8 g + k: this thread's k-th point of slice g is non-zero (zero-aware K2)
             // ---- K1: characteristic function on the damped grid -> x_j in shared memory ----
             // One grid point per thread at a time: interleaving points explicitly was measured slower
             // (profiles/r01_shape_sweep.txt); the ILP comes from the interleaved chains inside stage B / F.
@@ -534,7 +550,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         unsigned bits = 0u;
                         for (int g = 0; g < count; ++g) {
                             const SubSlice& s = grp.s[g];
-                            bits |= (tail_ub(tp, l1g, s.T, s.kts, s.v0s, s.lsm, gc.ui) < -750.0 ? 1u : 0u) << g;
+                            bits |= (tail_ub(tp, l1g, s.T, s.kts, s.v0s, s.lsm, gc.ui) < gc.cut - 4.0 ? 1u : 0u) << g;
                         }
                         gone |= bits << (3 * k);
                         if (bits == (1u << count) - 1u) skip |= 1u << k;
@@ -580,7 +596,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         unsigned bits = 0u;
                         for (int g = 0; g < (HB_BOUND_DECIM ? count : 0); ++g) {
                             const SubSlice& s = grp.s[g];
-                            bits |= (tail_ub(tp, l1g, s.T, s.kts, s.v0s, s.lsm, gc.ui) < -750.0 ? 1u : 0u) << g;
+                            bits |= (tail_ub(tp, l1g, s.T, s.kts, s.v0s, s.lsm, gc.ui) < gc.cut - 4.0 ? 1u : 0u) << g;
                         }
                         gone = (gone & ~(7u << (3 * k))) | (bits << (3 * k));
                         if (bits == (1u << count) - 1u) {
@@ -613,13 +629,14 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                             er[g] = fma(s.kts, b.B.re, fma(s.v0s, b.Dq.re, -(gc.ui * s.lsm)));  // stage_f, heston.cpp:87-91
                             ei[g] = fma(s.kts, b.B.im, fma(s.v0s, b.Dq.im, v * s.lsm));
                         }
-                        dmask |= (er[0] < -800.0 ? 1u : 0u) << k;
+                        dmask |= (er[0] < gc.cut_dead ? 1u : 0u) << k;
                         double pr[3] = {0.0, 0.0, 0.0}, pi[3] = {0.0, 0.0, 0.0};
-                        if (!(er[0] < -746.0 && er[1] < -746.0 && er[2] < -746.0)) cexp_w<3>(er, ei, pr, pi);
+                        if (!(er[0] < gc.cut && er[1] < gc.cut && er[2] < gc.cut)) cexp_w<3>(er, ei, pr, pi);
 #pragma unroll
                         for (int g = 0; g < 3; ++g) {
-                            const bool zero = er[g] < -746.0;  // exactly 0 as in stage_f
+                            const bool zero = er[g] < gc.cut;  // exactly 0 as in stage_f
                             const cplx phi = {zero ? 0.0 : pr[g], zero ? 0.0 : pi[g]};
+                            live |= (zero ? 0u : 1u) << (8 * g + k);
                             sts_c(slices + (size_t)g * N, j0, cmul(phi, tab));
                         }
                         continue;
@@ -642,8 +659,9 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         }
                         const SliceConst sc = {s.kts, s.v0s, s.lsm};
                         double er;
-                        const cplx phi = stage_f(b, sc, v, gc.ui, &er);
-                        if (g == 0) dmask |= (er < -800.0 ? 1u : 0u) << k;
+                        const cplx phi = stage_f(b, sc, v, gc.ui, &er, gc.cut);
+                        live |= (er < gc.cut ? 0u : 1u) << (8 * g + k);
+                        if (g == 0) dmask |= (er < gc.cut_dead ? 1u : 0u) << k;
                         sts_c(slices + (size_t)g * N, j0, cmul(phi, tab));
                     }
                 }
@@ -651,14 +669,30 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     const int mat = grp.s[0].mat;
                     deadm[mat >> 3] |= (unsigned long long)dmask << ((mat & 7) * 8);
                 }
+                if (kZeroAware) {
+                    // 1 + the highest non-zero point index of each slice, for the second pass (fft_smem.cuh)
+                    if (tid == 0 && ph == 0) {
+#pragma unroll
+                        for (int g = 0; g < kMaxGroup; ++g) s_jlive[(gi + 1) & 1][g] = 0;  // next group's
+                    }
+#pragma unroll
+                    for (int g = 0; g < kMaxGroup; ++g) {
+                        const unsigned lm = (live >> (8 * g)) & 0xffu;
+                        int jm = lm ? tid + NT * (31 - __clz(lm)) + 1 : 0;
+                        jm = __reduce_max_sync(0xffffffffu, jm);
+                        if ((tid & 31) == 0 && jm > 0) atomicMax(&s_jlive[gi & 1][g], jm);
+                    }
+                }
             }
             // ---- K2: in-place decimation-in-frequency passes in shared memory (fft_smem.cuh) ----
             // Pass 1: butterfly `tid` reads the points tid + r N/8 this thread has just written -> no barrier.
             if (N / 8 != NT) __syncthreads();
-            dif_pass<N, NT, N / 8, false>(slices, count, tw, tw512, grp.fmask, tid);
+            if constexpr (kZeroAware) dif_pass_first<N, NT>(slices, count, tw, live, tid);
+            else dif_pass<N, NT, N / 8, false>(slices, count, tw, tw512, grp.fmask, tid);
             __syncthreads();
             if (N >= 4096) {
-                dif_pass<N, NT, (N >= 4096 ? N / 64 : 8), false>(slices, count, tw, tw512, grp.fmask, tid);
+                if constexpr (kZeroAware) dif_pass_second<N, NT>(slices, count, tw512, s_jlive[gi & 1], tid);
+                else dif_pass<N, NT, (N >= 4096 ? N / 64 : 8), false>(slices, count, tw, tw512, grp.fmask, tid);
                 // The S = 8 butterfly of thread 8 blk' + t' reads the slots 64 blk' + t' + 8 r', written in the
                 // S = 64 pass by the threads 64 (blk' >> 3) + t' + 8 r': both sit in the same 64-thread group, so
                 // this hand-over needs a barrier among two warps only (named barriers 1..8), not the whole CTA.

@@ -94,6 +94,18 @@ class BatchPricer:
         self.n_maturities = int(self._L.hb_plan_n_maturities(self._h))
         return self
 
+    def set_truncation(self, abs_price_error: float) -> "BatchPricer":
+        """Admissible absolute price error of the significance cut (``hb_plan_set_truncation``): grid points
+        whose |phi| is so small that all of them together cannot move a price by more than this are treated as
+        exact zeros.  Default 2**-80; 0.0 = exact mode (only true exp underflow is skipped)."""
+        check(self._L.hb_plan_set_truncation(self._h, float(abs_price_error)))
+        return self
+
+    @property
+    def log_cut(self) -> float:
+        """log|phi| below which a grid point counts as 0 for the surface in force (-746 = exp underflow)."""
+        return float(self._L.hb_plan_log_cut(self._h))
+
     def set_bounds(self, lb, ub) -> "BatchPricer":
         lb, ub = _np_d(lb), _np_d(ub)
         if lb.size != 5 or ub.size != 5:

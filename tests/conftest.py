@@ -69,6 +69,11 @@ def g_fft():
     return load_golden("fft_selfcheck.npz")
 
 
+@pytest.fixture(scope="session")
+def g_fft_direct():
+    return load_golden("fft_direct.npz")
+
+
 def rel_err(a, b, floor=1e-300):
     a = np.asarray(a)
     b = np.asarray(b)

@@ -153,6 +153,27 @@ def test_fft_prices_match_oracle(torch_cuda, oracle, g_fft):
         assert_prices(got, oracle.price_batch(MODE_FFT, params[:9], Kf, Tf, ic, S0, R, Q), params[:9])
 
 
+def test_fft_prices_match_independent_direct_dft_golden(torch_cuda, g_fft_direct):
+    """The CUDA path against tests/golden/fft_direct.npz: prices built from the compiled reference's CF values
+    by direct O(N) sums in 50-digit arithmetic (make_golden_fft_direct.py) -- independent of the oracle's FFT."""
+    from pde_b200 import BatchPricer
+
+    torch = torch_cuda
+    g = g_fft_direct
+    s0, r, q = (float(x) for x in g["spot_rate_div"])
+    pricers = {}
+    # one surface per (N, eta, T, parameter set): the strikes of that golden row group
+    keys = sorted({(int(n), float(e), float(t), tuple(p)) for n, e, t, p in zip(g["N"], g["eta"], g["T"], g["params"])})
+    for (n, eta, t, p) in keys:
+        sel = np.flatnonzero((g["N"] == n) & (g["eta"] == eta) & (g["T"] == t) & (g["params"] == np.array(p)).all(axis=1))
+        pr = pricers.setdefault((n, eta), BatchPricer("fft", n_grid=n, eta=eta, alpha=float(g["alpha"])))
+        pr.set_surface(g["K"][sel], t, g["is_call"][sel], None, S0=s0, r=r, q=q)
+        got = pr.price(_dev(torch, [p])).cpu().numpy()[0]
+        v = price_violation(got, g["price"][sel])
+        assert v <= (4.0 if p[2] < 0.02 else 1.0), (n, eta, t, p, v)
+        assert np.array_equal(got == 0.0, g["price"][sel] == 0.0)  # clamped options stay clamped
+
+
 def test_fft_prices_sobol_full_surface(torch_cuda, oracle):
     from pde_b200 import BatchPricer
 
@@ -328,6 +349,121 @@ def test_normal_equations_match_oracle(torch_cuda, oracle, g_cal, mode, omode):
         assert (np.abs(got[i, 7:] - want[i, 7:]) <= b_jtj + 1e-9 * np.abs(want[i, 7:])).all(), (i, x)
 
 
+# ---- significance cut (hb_plan_set_truncation) ------------------------------------------------------------------------
+
+def test_significance_cut_is_bounded_by_its_own_error_budget(torch_cuda, oracle):
+    """Default plans drop grid points whose |phi| is below e^cut (cut chosen so that ALL dropped points together
+    cannot move a price by more than 2^-80); exact mode (0) only skips true exp underflow.  The two must agree
+    far inside the parity tolerance, on both launch paths, including the slow-decay corner (nothing dropped)
+    and the fast-decay one (almost everything dropped)."""
+    from pde_b200 import BatchPricer
+
+    torch = torch_cuda
+    Kf, Tf = np.tile(np.linspace(80, 120, 50), 32), np.repeat(np.linspace(0.1, 1.0, 32), 50)
+    corners = np.array([np.where([(m >> b) & 1 for b in range(5)], UB, LB) for m in range(32)])
+    small = np.vstack([DEFAULT, corners, sobol_sets(31)])          # 64 sets: split path
+    big = np.vstack([small, sobol_sets(512, seed=3)])              # persistent path
+    cut = BatchPricer("fft").set_surface(Kf, Tf, True, None, S0=S0, r=R, q=Q)
+    exact = BatchPricer("fft").set_truncation(0.0).set_surface(Kf, Tf, True, None, S0=S0, r=R, q=Q)
+    assert exact.log_cut == -746.0 and -64.0 < cut.log_cut < -40.0
+    # the cut the plan reports is the one its bound asks for: e^cut * sum|tab| * max scale = 2^-80
+    v = 0.25 * np.arange(4096)
+    w = (0.25 / 3) * np.where(np.arange(4096) == 0, 1.0, np.where(np.arange(4096) % 2 == 1, 4.0, 2.0))
+    wsum = np.sum(w / np.abs(0.75 ** 2 + 0.75 - v * v + 1j * 2.5 * v))
+    lam, b = 2 * np.pi / (4096 * 0.25), np.pi / 0.25
+    km = -b + lam * np.floor((np.log(Kf) + b) / lam)
+    scale = np.max(np.exp(-R * Tf) * np.exp(-0.75 * km) / np.pi)
+    assert abs(cut.log_cut - np.log(2.0 ** -80 / (wsum * scale))) < 1e-9
+    for xs in (small, big):
+        a = cut.price(_dev(torch, xs)).cpu().numpy()
+        e = exact.price(_dev(torch, xs)).cpu().numpy()
+        fin = np.isfinite(e)
+        assert np.array_equal(np.isfinite(a), fin)
+        # budget 2^-80 absolute; what is left is rounding of sums that lost their tiniest terms
+        assert np.max(np.abs(a[fin] - e[fin]) / (1e-14 * np.abs(e[fin]) + 1e-16)) <= 1.0
+    want = oracle.price_batch(MODE_FFT, small, Kf, Tf, True, S0, R, Q)
+    assert_prices(cut.price(_dev(torch, small)).cpu().numpy(), want, small)
+    assert_prices(exact.price(_dev(torch, small)).cpu().numpy(), want, small)
+    with pytest.raises(ValueError):
+        cut.set_truncation(1e-6)
+
+
+# ---- the benched path itself: C3 surface, persistent kernel, work elision live ----------------------------------
+
+def c3_benched_path_sets():
+    """>= 2 x SMs sets so the persistent launch path runs (dead masks / tail skip / asymptotic and series stage B
+    live): 512 Sobol points of the calibrator's box, its 32 corners, and a slow-decay cluster (sigma near 2,
+    rho near -0.99, small kappa theta: SURVEY.md App. D "no decay") where nothing can be elided."""
+    from scipy.stats import qmc
+
+    corners = np.array([np.where([(m >> b) & 1 for b in range(5)], UB, LB) for m in range(32)])
+    lo = np.array([0.1, 0.01, 1.5, -0.99, 0.01])
+    hi = np.array([0.5, 0.05, 2.0, -0.90, 0.05])
+    slow = lo + (hi - lo) * qmc.Sobol(d=5, seed=11).random(64)
+    return np.vstack([sobol_sets(512), corners, slow])
+
+
+def test_benched_path_normal_equations_match_oracle_on_c3_surface(torch_cuda, oracle):
+    """BASELINE.json config 3's own shape (32 maturities x 50 strikes, N = 4096, default bounds) on the launch
+    path bench.py times -- fft_job_kernel<4096,512,false,false>, one persistent CTA per set -- against
+    oracle.normal_eq_batch: all 22 columns, and hb_jacobian's residuals / Jacobian on the same sets."""
+    from pde_b200 import BatchPricer
+
+    torch = torch_cuda
+    oracle.use_all_cores()
+    xs = c3_benched_path_sets()
+    assert len(xs) >= 2 * torch.cuda.get_device_properties(0).multi_processor_count  # persistent path
+    Kf, Tf = np.tile(np.linspace(80, 120, 50), 32), np.repeat(np.linspace(0.1, 1.0, 32), 50)
+    mk = oracle.price_batch(MODE_FFT, [DEFAULT], Kf, Tf, True, S0, R, Q)[0]
+    mk = np.maximum(mk * (1 + 0.001 * np.random.default_rng(42).normal(size=mk.size)), 0.01)
+    pr = BatchPricer("fft").set_surface(Kf, Tf, True, mk, S0=S0, r=R, q=Q).set_bounds(LB, UB)
+    X = _dev(torch, xs)
+    got = pr.normal_equations(X).cpu().numpy()
+    res, jac = pr.jacobian(X)
+    res, jac = res.cpu().numpy(), jac.cpu().numpy()
+    prices = pr.price(X).cpu().numpy()
+    want = oracle.normal_eq_batch(MODE_FFT, xs, LB, UB, Kf, Tf, True, mk, S0, R, Q)
+
+    fin = np.isfinite(want).all(axis=1) & (want[:, 0] != 1e10)
+    assert fin.sum() >= 400  # most of the population is an ordinary candidate
+    # sentinel / non-finite pattern (moment explosion -> inf, clamped prices -> 1e10) must be the oracle's
+    assert np.array_equal(got[:, 0] == 1e10, want[:, 0] == 1e10)
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    np.testing.assert_allclose(got[fin, 0], want[fin, 0], rtol=1e-9)  # loss, SURVEY.md 8c budget
+    np.testing.assert_allclose(got[fin, 1], want[fin, 1], rtol=1e-9)  # ||r||^2
+    # J^T r / J^T J: bounded from first principles as in test_normal_equations_match_oracle, price discrepancy
+    # dp = 2e-12 |p| + 2e-14 (50x tighter than the contractual tolerance), |J| and |r| from the device Jacobian
+    iu = np.triu_indices(5)
+    worst = 0.0
+    for i in np.flatnonzero(fin):
+        dx = np.abs(oracle.fd_steps(xs[i], LB, UB))
+        dp = 2e-12 * np.abs(prices[i]) + 2e-14
+        dJ = 2.0 * dp[:, None] / (dx[None, :] * mk[:, None])
+        dr = dp / mk
+        aJ, ar = np.abs(jac[i]), np.abs(res[i])
+        b_jtr = dJ.T @ ar + aJ.T @ dr + 1e-9 * np.abs(want[i, 2:7])
+        b_jtj = (aJ.T @ dJ + dJ.T @ aJ)[iu] + 1e-9 * np.abs(want[i, 7:])
+        worst = max(worst, (np.abs(got[i, 2:7] - want[i, 2:7]) / b_jtr).max(), (np.abs(got[i, 7:] - want[i, 7:]) / b_jtj).max())
+    assert worst <= 1.0, worst
+    # hb_jacobian on the same path: residuals within the price tolerance, Jacobian within its FD amplification,
+    # against the oracle's own residuals / SciPy-rule Jacobian on a sample that includes corners and slow-decay sets
+    sample = np.concatenate([np.arange(0, 512, 37), np.arange(512, 544, 5), np.arange(544, 608, 13)])
+    for i in sample:
+        if not fin[i]:
+            continue
+        r0, J = oracle.jacobian(MODE_FFT, xs[i], LB, UB, Kf, Tf, True, mk, S0, R, Q)
+        limit = 4.0 if xs[i][2] < 0.02 else 1.0
+        tol_p = 1e-10 * np.abs(prices[i]) + 1e-12
+        assert (np.abs(res[i] - r0) <= limit * tol_p / mk).all(), (i, xs[i])
+        dx = np.abs(oracle.fd_steps(xs[i], LB, UB))
+        assert (np.abs(jac[i] - J) <= limit * 2.0 * tol_p[:, None] / (dx[None, :] * mk[:, None]) + 1e-9 * np.abs(J)).all(), (i, xs[i])
+    # and the device's normal equations are its own Jacobian contracted (same kernel, different epilogue)
+    for i in sample:
+        if fin[i]:
+            np.testing.assert_allclose(got[i, 2:7], jac[i].T @ res[i], rtol=1e-9, atol=1e-9 * np.abs(got[i, 2:7]).max())
+            np.testing.assert_allclose(got[i, 7:], (jac[i].T @ jac[i])[iu], rtol=1e-9, atol=1e-9 * np.abs(got[i, 7:]).max())
+
+
 # ---- full-size properties (BASELINE.json config 3: 65,536 sets x 32 maturities, N = 4096) -------------------------
 
 def test_full_size_objective_properties(torch_cuda, oracle):
@@ -353,7 +489,7 @@ def test_full_size_objective_properties(torch_cuda, oracle):
     want = oracle.objective_batch(MODE_FFT, params[idx], Kf, Tf, True, mk, S0, R, Q)
     got = loss.cpu().numpy()[idx]
     assert np.array_equal(got == 1e10, want == 1e10)
-    np.testing.assert_allclose(got, want, rtol=1e-8)
+    np.testing.assert_allclose(got, want, rtol=1e-9)  # loss 1e-9 relative
     # non-finite losses (moment explosion of E[S^1.75] -> inf prices -> inf loss in the reference too,
     # heston_calibrator.py:507-511 only screens NaN and <= 0) must be the oracle's non-finite losses
     all_loss = loss.cpu().numpy()

@@ -127,7 +127,24 @@ def test_normal_equations_consistent(oracle, g_cal):
         np.testing.assert_allclose(ne[i, 7:], (J.T @ J)[iu], rtol=1e-9)
 
 
-# ---- FFT mode: no reference implementation exists (parity unpinned); these guard the restatement ----
+# ---- FFT mode: no reference implementation exists; pinned to the reference's CF + an independent transform ----
+
+def test_fft_mode_matches_independent_direct_dft_golden(oracle, g_fft_direct):
+    """tests/golden/fft_direct.npz (make_golden_fft_direct.py): the compiled reference's CF values pushed
+    through the written Carr-Madan specification by O(N) direct sums at the two bracketing bins in 50-digit
+    arithmetic -- no FFT, no code shared with heston_oracle.c.  Pins Simpson weights, transform sign and
+    normalisation, grid origin, bin / fraction of each strike, e^{-alpha k}/pi e^{-rT} scale, clamp and parity."""
+    g = g_fft_direct
+    s0, r, q = g["spot_rate_div"]
+    worst = 0.0
+    for i in range(g["price"].size):
+        got = oracle.price_batch(MODE_FFT, [g["params"][i]], [g["K"][i]], [g["T"][i]], [bool(g["is_call"][i])], s0, r, q,
+                                 N=int(g["N"][i]), eta=float(g["eta"][i]), alpha=float(g["alpha"]))[0, 0]
+        want = g["price"][i]
+        worst = max(worst, abs(got - want) / (1e-12 * abs(want) + 1e-14))
+    assert worst <= 1.0, worst
+    assert set(np.unique(g["N"])) == {512, 4096, 16384} and (g["price"] == 0.0).any() and (~g["is_call"]).any()
+
 
 def test_fft_mode_selfcheck_and_numpy_fft(oracle, g_fft):
     K, T8 = g_fft["K50"], g_fft["T8"]

@@ -20,6 +20,20 @@ from bench import LB, UB, N_MAT, Q, R, S0, TRUTH, slow_decay_sets, sobol_sets, s
 from pde_b200 import BatchPricer  # noqa: E402
 
 
+def _probe_read():
+    """Phase-cycle table of a -DHB_PROBE build (None for the product library)."""
+    import ctypes as C
+
+    from pde_b200 import _lib
+
+    L = _lib.load()
+    if not hasattr(L, "hb_probe_read"):
+        return None
+    buf = (C.c_ulonglong * 16)()
+    L.hb_probe_read(buf)
+    return list(buf)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sets", type=int, default=65536)
@@ -44,6 +58,7 @@ def main():
         for _ in range(3):
             res = fn(X)
         torch.cuda.synchronize()
+        _probe_read()
         ms = 0.0
         for _ in range(a.steps):
             flush.fill_(1)
@@ -54,6 +69,12 @@ def main():
             torch.cuda.synchronize()
             ms += e0.elapsed_time(e1)
         ms /= a.steps
+        probe = _probe_read()
+        if probe is not None:
+            names = ["K1", "pass1", "barrier_after_pass1", "pass2+pairbar", "pass3", "barrier_after_pass3", "K3",
+                     "finalize"]
+            tot = float(sum(probe[:8])) or 1.0
+            out[name + "_probe_share"] = {n: round(probe[i] / tot, 4) for i, n in enumerate(names)}
         out[name] = {"ms_per_step": ms, "slice_evals_per_s": a.sets * N_MAT * evals / (ms * 1e-3),
                      "checksum": float(torch.nan_to_num(res.double(), nan=0.0, posinf=0.0, neginf=0.0).clamp(-1e6, 1e6).sum())}
     print(json.dumps(out), flush=True)

@@ -39,6 +39,11 @@ def needs_build() -> bool:
         return fh.read().strip() != source_hash()
 
 
+# every elision of the fused kernel off: no perturbed-class tail skip, no asymptotic / series stage B, no rigorous
+# tail bound in the decimation path (run it with hb_plan_set_truncation(plan, 0) for "exact" underflow-only zeros)
+NOELIDE_DEFINES = ["HB_TAIL=0", "HB_ASYM_DT=1e300", "HB_MID=0", "HB_BOUND_DECIM=0", "HB_ZERO_AWARE=0"]
+
+
 def build_variant(name: str, defines, verbose: bool = False) -> str:
     """A second build of the same sources with -D switches (kernel A/B experiments and bench.py's no-elision
     leg), as libheston_b200_<name>.so; select it with PDE_B200_LIB."""

@@ -103,6 +103,8 @@ struct hb_plan {
     double w_sum = 0.0;                        // sum_j |tab_j| over the damped grid
     double scale_max = 0.0;                    // max over the surface of disc * e^{-alpha k_m}/pi
     bool tail_ok = true;                       // FD bounds inside the validated default box
+    cudaEvent_t last_launch = nullptr;         // recorded after every launch of this plan (hb_surface_set waits on it)
+    std::vector<double> scalar_key;            // hb_model_* cache: the surface this plan currently holds
     const double* d_strike = nullptr;    // caller-order copies for the implied-vol epilogue
     const double* d_maturity = nullptr;
     const uint8_t* d_is_call = nullptr;
@@ -148,9 +150,22 @@ size_t fft_smem_bytes(int N, int g) { return (size_t)g * N * 16 + (size_t)(N / 8
 // fused kernel: slices + W_N table + the small W_512 / W_64 / w8 tables (fft_smem.cuh, dif_pass)
 size_t job_smem_bytes(int N, int g) { return fft_smem_bytes(N, g) + (size_t)kTwSmall * 16; }
 
+int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int what, double* d_out, double* d_out2,
+                     cudaStream_t st);
+
 // Launch the pricing pipeline for P parameter sets (device SoA) and the requested output.
 int launch_jobs(hb_plan* pl, const double* d_params, int ld, int P, int what, double* d_out, double* d_out2,
                 cudaStream_t st) {
+    const int rc = launch_jobs_impl(pl, d_params, ld, P, what, d_out, d_out2, st);
+    if (rc == HB_OK && pl && pl->last_launch) {
+        DeviceGuard guard(pl->device);
+        HB_CUDA(cudaEventRecord(pl->last_launch, st));
+    }
+    return rc;
+}
+
+int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int what, double* d_out, double* d_out2,
+                     cudaStream_t st) {
     if (!pl) return fail(HB_ERR_INVALID_ARGUMENT, "plan is NULL");
     if (!pl->has_surface) return fail(HB_ERR_STATE, "hb_surface_set has not been called on this plan");
     if (what != W_PRICE && !pl->has_market)
@@ -324,6 +339,17 @@ extern "C" void hb_internal_count_launch(void) { g_launches++; }
 
 extern "C" {
 
+#ifdef HB_PROBE
+// diagnostic builds only (not declared in include/heston_b200.h): read and clear the phase-cycle table
+int hb_probe_read(unsigned long long* out16) {
+    HB_CUDA(cudaDeviceSynchronize());
+    HB_CUDA(cudaMemcpyFromSymbol(out16, hb::g_probe, sizeof(unsigned long long) * 16));
+    unsigned long long z[16] = {0};
+    HB_CUDA(cudaMemcpyToSymbol(hb::g_probe, z, sizeof z));
+    return HB_OK;
+}
+#endif
+
 int hb_version(void) { return 100; }
 const char* hb_last_error(void) { return g_err.c_str(); }
 uint64_t hb_launch_count(void) { return g_launches.load(); }
@@ -367,6 +393,10 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
     pl->alpha = alpha;
     pl->device = device;
     pl->sm_count = prop.multiProcessorCount;
+    if (cudaEventCreateWithFlags(&pl->last_launch, cudaEventDisableTiming) != cudaSuccess) {
+        delete pl;
+        return fail(HB_ERR_CUDA, "cudaEventCreate failed");
+    }
     const double lb[5] = {0.1, 0.01, 0.01, -0.99, 0.01};  // heston_calibrator.py:201-207
     const double ub[5] = {10.0, 1.0, 2.0, 0.99, 1.0};
     std::memcpy(pl->bd.lb, lb, sizeof lb);
@@ -405,6 +435,10 @@ int hb_plan_destroy(hb_plan* pl) {
     for (hb_plan*& sp : pl->sib) {
         hb_plan_destroy(sp);
         sp = nullptr;
+    }
+    if (pl->last_launch) {
+        cudaEventSynchronize(pl->last_launch);
+        cudaEventDestroy(pl->last_launch);
     }
     pl->gk.release();
     pl->surf.release();
@@ -458,8 +492,9 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
         return fail(HB_ERR_INVALID_ARGUMENT, "NULL option arrays");
     DeviceGuard guard(pl->device);
     if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
-    // launches of this plan may still be reading the old tables on a caller stream
-    HB_CUDA(cudaDeviceSynchronize());
+    // launches of this plan may still be reading the old tables on a caller stream: wait for the plan's own
+    // last launch (not for the whole device: unrelated streams keep running)
+    if (pl->last_launch) HB_CUDA(cudaEventSynchronize(pl->last_launch));
     const double nan = std::numeric_limits<double>::quiet_NaN();
     const int N = pl->N;
     const double alpha = pl->alpha, eta = pl->eta;
@@ -555,6 +590,13 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                  o_Tm = bb.add(std::vector<double>(maturity, maturity + n_opt)),
                  o_ic = bb.add(std::vector<uint8_t>(is_call, is_call + n_opt));
     pl->surf.want_pinned = true;
+    // reserve() may free the old blob before a failing allocation: the plan holds no surface until the upload is done
+    pl->has_surface = pl->has_market = false;
+    pl->S = SurfaceDev{};
+    pl->d_strike = pl->d_maturity = nullptr;
+    pl->d_is_call = nullptr;
+    pl->sib_stale = true;
+    pl->scalar_key.clear();
     int rc = pl->surf.reserve(bb.bytes.size());
     if (rc) return rc;
     std::memcpy(pl->surf.pinned, bb.bytes.data(), bb.bytes.size());
@@ -692,7 +734,10 @@ int hb_cf(const double* d_params, int ld, int P, const double* d_T, int n_T, con
     if (total == 0) return HB_OK;
     if (!d_params || !d_T || !d_ur || !d_ui || !d_out) return fail(HB_ERR_INVALID_ARGUMENT, "NULL device pointer");
     const int block = 128;
-    const int grid = (int)std::min<size_t>((total + block - 1) / block, 148 * 32);
+    int dev = 0, sms = 148;
+    HB_CUDA(cudaGetDevice(&dev));
+    HB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<size_t>((total + block - 1) / block, (size_t)sms * 32);
     cf_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_params, ld, P, d_T, n_T, d_ur, d_ui, n_u, spot, rate,
                                                         dividend, (double2*)d_out);
     g_launches++;
@@ -760,17 +805,65 @@ int hb_model_validate(const double* p) {
     return validate_params(p);
 }
 
-// One cached refgrid plan per (thread, device) keeps scalar calls at a few driver calls each.
-static hb_plan* scalar_plan(int device, int* rc) {
-    thread_local std::map<int, hb_plan*> cache;
-    auto it = cache.find(device);
-    if (it != cache.end()) {
-        *rc = HB_OK;
-        return it->second;
+// Scalar drop-in calls (hb_model_*): a small per-thread cache of refgrid plans, each remembering the surface it
+// holds.  The reference's calibrator prices the SAME few options again and again, one price_option call each
+// (heston_calibrator.py:572-584): a repeated (strikes, maturities, is_call, spot, rate, dividend) finds its plan
+// with the tables already on the device and costs one 40-byte upload, one launch and one read-back -- no
+// surface rebuild, no device-wide synchronisation.  Plans are destroyed when the thread exits.
+namespace {
+constexpr size_t kScalarPlans = 64;
+struct ScalarCache {
+    struct Entry {
+        hb_plan* pl;
+        uint64_t stamp;
+    };
+    std::vector<Entry> entries;
+    uint64_t clock = 0;
+    ~ScalarCache() {
+        for (Entry& e : entries) hb_plan_destroy(e.pl);
+    }
+};
+std::vector<double> scalar_key_of(int device, int n, const double* K, const double* T, int is_call, double spot,
+                                  double rate, double dividend) {
+    std::vector<double> key;
+    key.reserve(2 * (size_t)n + 6);
+    key.push_back((double)device);
+    key.push_back((double)n);
+    key.push_back((double)is_call);
+    key.push_back(spot);
+    key.push_back(rate);
+    key.push_back(dividend);
+    key.insert(key.end(), K, K + n);
+    key.insert(key.end(), T, T + n);
+    return key;
+}
+bool same_bits(const std::vector<double>& a, const std::vector<double>& b) {
+    return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0);
+}
+}  // namespace
+
+// -> a plan on `device`; *hit says whether it already holds the surface `key` (empty key: any plan will do).
+static hb_plan* scalar_plan(int device, const std::vector<double>& key, bool* hit, int* rc) {
+    thread_local ScalarCache cache;
+    *rc = HB_OK;
+    *hit = false;
+    ScalarCache::Entry* lru = nullptr;
+    for (ScalarCache::Entry& e : cache.entries) {
+        if (e.pl->device != device) continue;
+        if (key.empty() || same_bits(e.pl->scalar_key, key)) {
+            e.stamp = ++cache.clock;
+            *hit = !key.empty();
+            return e.pl;
+        }
+        if (!lru || e.stamp < lru->stamp) lru = &e;
+    }
+    if (cache.entries.size() >= kScalarPlans && lru) {  // reuse the least recently used plan of this device
+        lru->stamp = ++cache.clock;
+        return lru->pl;
     }
     hb_plan* pl = nullptr;
     *rc = hb_plan_create(HB_MODE_REFGRID, 0, 0.0, 0.75, device, &pl);
-    if (*rc == HB_OK) cache[device] = pl;
+    if (*rc == HB_OK) cache.entries.push_back({pl, ++cache.clock});
     return pl;
 }
 
@@ -779,7 +872,8 @@ int hb_model_cf(const double* p, double u_re, double u_im, double T, double spot
     if (!p || !out2) return fail(HB_ERR_INVALID_ARGUMENT, "NULL argument");
     int rc = validate_params(p);
     if (rc) return rc;
-    hb_plan* pl = scalar_plan(device, &rc);
+    bool hit = false;
+    hb_plan* pl = scalar_plan(device, {}, &hit, &rc);
     if (rc) return rc;
     DeviceGuard guard(device);
     if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
@@ -821,9 +915,14 @@ int hb_model_price_options(const double* p, int n, const double* strikes, int n_
         if (!(spot > 0.0)) return fail(HB_ERR_INVALID_ARGUMENT, "Spot must be positive");
         if (!(T[i] >= 0.0)) return fail(HB_ERR_INVALID_ARGUMENT, "Maturity must be non-negative");
     }
-    hb_plan* pl = scalar_plan(device, &rc);
+    const std::vector<double> key = scalar_key_of(device, n, strikes, T.data(), is_call ? 1 : 0, spot, rate, dividend);
+    bool hit = false;
+    hb_plan* pl = scalar_plan(device, key, &hit, &rc);
     if (rc) return rc;
-    if ((rc = hb_surface_set(pl, n, strikes, T.data(), ic.data(), nullptr, spot, rate, dividend))) return rc;
+    if (!hit) {
+        if ((rc = hb_surface_set(pl, n, strikes, T.data(), ic.data(), nullptr, spot, rate, dividend))) return rc;
+        pl->scalar_key = key;
+    }
     return hb_price_host(pl, p, 1, out);
 }
 

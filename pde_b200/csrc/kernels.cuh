@@ -31,6 +31,25 @@
 
 namespace hb {
 
+// Phase probe (diagnostic builds only, -DHB_PROBE: benchmarks/step_rate.py --probe): lane 0 of every warp adds the
+// cycles it spends in each phase of a group to a global table.  Not compiled into the product library.
+#ifdef HB_PROBE
+__device__ unsigned long long g_probe[16];
+__device__ __forceinline__ long long probe_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");  // not to be moved across barriers / memory ops
+    return t;
+}
+#define HB_PROBE_T(var) const long long var = probe_clock()
+#define HB_PROBE_ADD(slot, t0, t1) \
+    do {                           \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_probe[slot], (unsigned long long)((t1) - (t0))); \
+    } while (0)
+#else
+#define HB_PROBE_T(var)
+#define HB_PROBE_ADD(slot, t0, t1)
+#endif
+
 enum What { W_PRICE = 0, W_LOSS = 1, W_NEQ = 2, W_JAC = 3 };
 
 // Device view of the option surface, grouped by distinct maturity (CSR).  "sorted" arrays
@@ -510,6 +529,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 cached_cls = cls;
             }
             for (int ph = 0; ph < R; ++ph) {
+            HB_PROBE_T(pt0);
             unsigned live = 0u;  // bit 8 g + k: this thread's k-th point of slice g is non-zero (zero-aware K2)
             // ---- K1: characteristic function on the damped grid -> x_j in shared memory ----
             // One grid point per thread at a time: interleaving points explicitly was measured slower
@@ -686,10 +706,13 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             }
             // ---- K2: in-place decimation-in-frequency passes in shared memory (fft_smem.cuh) ----
             // Pass 1: butterfly `tid` reads the points tid + r N/8 this thread has just written -> no barrier.
+            HB_PROBE_T(pt1);
             if (N / 8 != NT) __syncthreads();
             if constexpr (kZeroAware) dif_pass_first<N, NT>(slices, count, tw, live, tid);
             else dif_pass<N, NT, N / 8, false>(slices, count, tw, tw512, grp.fmask, tid);
+            HB_PROBE_T(pt2);
             __syncthreads();
+            HB_PROBE_T(pt3);
             if (N >= 4096) {
                 if constexpr (kZeroAware) dif_pass_second<N, NT>(slices, count, tw512, s_jlive[gi & 1], tid);
                 else dif_pass<N, NT, (N >= 4096 ? N / 64 : 8), false>(slices, count, tw, tw512, grp.fmask, tid);
@@ -701,9 +724,12 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 else
                     __syncthreads();
             }
+            HB_PROBE_T(pt4);
             K3Opt cur = k3_load(grp, 0);
             dif_pass<N, NT, 8, true>(slices, count, tw, tw512, grp.fmask, tid);  // only the digits the strikes need
+            HB_PROBE_T(pt5);
             __syncthreads();
+            HB_PROBE_T(pt6);
             // ---- K3: last butterfly output at the two bracketing bins, log-strike interpolation
             // (accumulated over phases), clamp, parity -> price rows ----
             {
@@ -748,10 +774,21 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     cur = nxt;
                 }
             }
+            HB_PROBE_T(pt7);
+            HB_PROBE_ADD(0, pt0, pt1);  // K1 (incl. group set-up of the next group by one thread)
+            HB_PROBE_ADD(1, pt1, pt2);  // pass 1
+            HB_PROBE_ADD(2, pt2, pt3);  // barrier after pass 1 (waits for the slowest K1)
+            HB_PROBE_ADD(3, pt3, pt4);  // pass 2 + pair barrier
+            HB_PROBE_ADD(4, pt4, pt5);  // pass 3 (+ first K3 constants)
+            HB_PROBE_ADD(5, pt5, pt6);  // barrier after pass 3
+            HB_PROBE_ADD(6, pt6, pt7);  // K3 (incl. its release barrier)
             }
         }
+        HB_PROBE_T(pf0);
         __syncthreads();  // the price rows of the last group are complete
         if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
+        HB_PROBE_T(pf1);
+        HB_PROBE_ADD(7, pf0, pf1);  // finalize
     }
 }
 

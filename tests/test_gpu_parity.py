@@ -433,18 +433,25 @@ def test_benched_path_normal_equations_match_oracle_on_c3_surface(torch_cuda, or
     np.testing.assert_allclose(got[fin, 1], want[fin, 1], rtol=1e-9)  # ||r||^2
     # J^T r / J^T J: bounded from first principles as in test_normal_equations_match_oracle, price discrepancy
     # dp = 2e-12 |p| + 2e-14 (50x tighter than the contractual tolerance), |J| and |r| from the device Jacobian
+    # Small sigma (kappa theta / sigma^2 up to 1e5) is the documented conditioning corner where the REFERENCE's own
+    # double-precision CF loses digits (tests/test_conditioning.py): there dp is the contractual tolerance itself
+    # (1e-10 |p| + 1e-12, x4 below sigma = 0.02).  Measured on B200: worst 0.39 of that; everywhere else 0.52 of
+    # the 50x tighter bound.
     iu = np.triu_indices(5)
-    worst = 0.0
+    worst = [0.0, 0.0]
     for i in np.flatnonzero(fin):
+        small_sigma = xs[i][2] < 0.05
+        scale = (4.0 if xs[i][2] < 0.02 else 1.0) * 50.0 if small_sigma else 1.0
         dx = np.abs(oracle.fd_steps(xs[i], LB, UB))
-        dp = 2e-12 * np.abs(prices[i]) + 2e-14
+        dp = scale * (2e-12 * np.abs(prices[i]) + 2e-14)
         dJ = 2.0 * dp[:, None] / (dx[None, :] * mk[:, None])
         dr = dp / mk
         aJ, ar = np.abs(jac[i]), np.abs(res[i])
         b_jtr = dJ.T @ ar + aJ.T @ dr + 1e-9 * np.abs(want[i, 2:7])
         b_jtj = (aJ.T @ dJ + dJ.T @ aJ)[iu] + 1e-9 * np.abs(want[i, 7:])
-        worst = max(worst, (np.abs(got[i, 2:7] - want[i, 2:7]) / b_jtr).max(), (np.abs(got[i, 7:] - want[i, 7:]) / b_jtj).max())
-    assert worst <= 1.0, worst
+        w = max((np.abs(got[i, 2:7] - want[i, 2:7]) / b_jtr).max(), (np.abs(got[i, 7:] - want[i, 7:]) / b_jtj).max())
+        worst[int(small_sigma)] = max(worst[int(small_sigma)], w)
+        assert w <= 1.0, (i, xs[i], w)
     # hb_jacobian on the same path: residuals within the price tolerance, Jacobian within its FD amplification,
     # against the oracle's own residuals / SciPy-rule Jacobian on a sample that includes corners and slow-decay sets
     sample = np.concatenate([np.arange(0, 512, 37), np.arange(512, 544, 5), np.arange(544, 608, 13)])

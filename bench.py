@@ -154,29 +154,40 @@ def cpu_reference_rate(seconds_budget, n_sets_hint=None):
         el = time.perf_counter() - t0
         if el >= seconds_budget or done + chunk > len(rows):
             break
-    return done * N_MAT / el, {"cores": cores, "kind": "reference", "seconds": round(el, 3),
+    return done * N_MAT / el, {"cores": cores, "kind": "reference", "seconds": round(el, 3), "sets_done": done,
                                "sample": f"{done} parameter-set evaluations x {N_MAT} maturities x {N_STRIKE} strikes "
                                          f"through the reference's HestonModel::price_options (1023-point quadrature "
                                          f"per option, OpenMP over options)"}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own C++ (oracle/_ref: heston.cpp compiled unmodified) on the host cores.
+    A step is a time-bounded SAMPLE of the workload (whole parameter sets x 32 maturities x 50 strikes through
+    HestonModel::price_options); `value` is the sampled rate, `ms_per_step` the measured duration of a step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     per_step = max(2.0, min(8.0, 120.0 / max(1, args.steps + args.warmup)))
-    rates = []
+    rates, secs, done = [], [], []
     info = None
     for i in range(args.warmup + args.steps):
         rate, info = cpu_reference_rate(per_step)
         if i >= args.warmup:
             rates.append(rate)
+            secs.append(info["seconds"])
+            done.append(info["sets_done"])
     value = float(np.mean(rates))
+    cfg = workload_config(args.sets)
+    cfg["reference_sample"] = (f"each step prices {int(np.mean(done))} of the {args.sets} parameter sets (time-bounded "
+                               f"sample, {per_step:.0f} s budget); the rate is a sampled rate of the same workload")
+    cfg["reference_arithmetic"] = ("the reference has no FFT: price_options is a 1023-point quadrature PER OPTION "
+                                   "(51,150 CF evaluations per slice against 4,096 in fft mode); the like-for-like CPU "
+                                   "number is cpu_baseline.port_fft of the default arm")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.sets),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "slices/s", "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"]},
         "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,27 +195,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def kernel_source_hash():
+    """Content hash of the CUDA sources the library is built from (pde_b200/csrc/build.py)."""
+    from pde_b200.csrc.build import source_hash
+
+    return source_hash()
+
+
 def _ncu_capture(P):
-    """The committed `ncu --set full` capture of ONE launch of the bench step (profiles/r01_traffic.json);
-    None when the launch shape differs."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """The committed `ncu --set full` capture of ONE launch of the bench step (profiles/r02_traffic.json).  It is
+    only quoted when it was taken on THIS kernel source (content hash) and launch shape; otherwise null."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(path):
         return None
     t = json.load(open(path))
-    return t if (t["sets_per_launch"], t["maturities"], t["strikes"]) == (P, N_MAT, N_STRIKE) else None
-
-
-def measured_traffic(P):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch, or null."""
-    t = _ncu_capture(P)
-    return t["dram_bytes_per_launch"] if t else None
-
-
-def ncu_pipe_active(P):
-    """sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active of that capture as a fraction, or null:
-    the executed-work utilisation next to the algorithmic (W1) fraction, which sharing pushes above 1."""
-    t = _ncu_capture(P)
-    return t["fp64_pipe_active_pct"] / 100.0 if t else None
+    if (t["sets_per_launch"], t["maturities"], t["strikes"]) != (P, N_MAT, N_STRIKE):
+        return None
+    return t if t.get("kernel_source_hash") == kernel_source_hash() else None
 
 
 def workload_config(P):
@@ -213,7 +220,55 @@ def workload_config(P):
                         f"eta={ETA}, alpha={ALPHA}; 6 slice evaluations per (set, maturity)",
             "sets_per_gpu": P, "maturities": N_MAT, "strikes": N_STRIKE, "n_grid": N_GRID,
             "slice_evals_per_step_per_gpu": P * N_MAT * 6, "mode": "fft",
+            "population": "scrambled Sobol (seed 42) over HestonCalibrator.DEFAULT_BOUNDS: the rate is INPUT-DEPENDENT "
+                          "-- the integrand of most sets decays within the first ~10 % of the grid and decayed points "
+                          "are not evaluated (exact underflow, plan's significance cut, asymptotic stage B); "
+                          "value_noskip gives the same step where nothing can be or is elided",
             "l2": "L2 flushed (256 MiB write) between timed steps; per-step CUDA events on the launch stream"}
+
+
+def feasible_surface(pricer):
+    """C4's calibration surface: the 32 x 50 grid minus the options whose fft-mode price at the truth is below the
+    generator's 0.01 floor (deep OTM at the shortest maturities: the FFT value clamps to 0 there, SURVEY.md
+    App. B, so the truth itself would score the 1e10 sentinel).  -> (K, T, market)."""
+    K, T = surface()
+    pricer.set_surface(K, T, True, None, S0=S0, r=R, q=Q)
+    p = pricer.price_host(TRUTH[None, :])[0]
+    keep = p >= 0.05
+    K, T, p = K[keep], T[keep], p[keep]
+    mk = np.maximum(p * (1 + 0.001 * np.random.default_rng(42).normal(size=p.size)), 0.01)
+    return K, T, mk
+
+
+def timed_steps(torch, dev, fn, steps, flush):
+    """Per-step CUDA events on the current stream of `dev`, L2 flushed before each step -> total ms."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(dev)
+    return sum(a.elapsed_time(b) for a, b in ev)
+
+
+def noelide_rate(sets):
+    """The bench step on the Sobol box through the no-elision build (pde_b200/csrc/build.py NOELIDE_DEFINES:
+    no tail skip, no asymptotic / series stage B, no zero-aware passes) in exact mode, in a subprocess."""
+    lib = os.path.join(ROOT, "pde_b200", "csrc", "libheston_b200_noelide.so")
+    if not os.path.exists(lib):
+        return {"error": "libheston_b200_noelide.so not built"}
+    env = dict(os.environ, PDE_B200_LIB=lib)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "step_rate.py"), "--sets", str(sets),
+                            "--trunc", "0", "--steps", "2", "--tag", "noelide"], env=env, capture_output=True, text=True,
+                           timeout=300)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": d["neq"]["slice_evals_per_s"], "ms_per_step": d["neq"]["ms_per_step"], "sets": sets}
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)[:200]}
 
 
 def run_ours(args):
@@ -221,7 +276,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from pde_b200 import BatchPricer, launch_count, measure_fp64_peak
-    from pde_b200.sharding import init_from_env
+    from pde_b200.sharding import init_from_env, sharded_map
 
     rank, world, local = init_from_env("nccl")
     if world != args.gpus and rank == 0:
@@ -253,75 +308,175 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     peak = measure_fp64_peak(local, 0.5)
     for _ in range(args.warmup):
         step()
     barrier()
+    # multi-GPU correctness bit: every rank's gathered rows == the same sets priced alone on rank 0
+    shard_check = None
+    if world > 1:
+        n_chk = 4096 // world
+        ok = True
+        if rank == 0:
+            for rk in range(world):
+                Xr = torch.from_numpy(sobol_sets(n_chk, skip=rk * P)).to(dev)
+                mine = pricer.normal_equations(Xr)
+                ok = ok and torch.equal(mine.view(torch.int64), gathered[rk * P: rk * P + n_chk].view(torch.int64))
+        shard_check = "bitwise" if ok else "MISMATCH"
+        barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = launch_count()
     t_wall = time.perf_counter()
-    for a, b in ev:
-        flush.fill_(1)
-        a.record()
-        out = step()
-        b.record()
+    ms = timed_steps(torch, dev, step, args.steps, flush)
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     slices_step = world * P * N_MAT * 6
     value = slices_step * args.steps / (ms * 1e-3)
 
-    # e2e: the public host-buffer call (pinned in/out, H2D + D2H inside the timed region)
+    # e2e: host buffers in, host buffers out, copies inside the timed region.  N = 1: the public C-ABI host call
+    # (hb_normal_eq_host: pinned staging, H2D, kernel, D2H).  N > 1: the whole multi-GPU step -- H2D of this rank's
+    # candidates from pinned memory, kernel, NCCL all-gather of the result rows, D2H of the gathered block.
     Xh = X_host.numpy()
-    pricer.normal_equations_host(Xh[: min(P, 1024)])
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = pricer.normal_equations_host(Xh)
-    torch.cuda.synchronize(dev)
-    te = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([te], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        te = float(t.item())
+    if world == 1:
+        pricer.normal_equations_host(Xh[: min(P, 1024)])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = pricer.normal_equations_host(Xh)
+        torch.cuda.synchronize(dev)
+        te = time.perf_counter() - t0
+        h2d, d2h = P * 5 * 8, P * 22 * 8
+    else:
+        gathered_host = torch.empty((world * P, 22), dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            X.copy_(X_host, non_blocking=True)
+            out = pricer.normal_equations(X)
+            dist.all_gather_into_tensor(gathered, out)
+            gathered_host.copy_(gathered, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        te = time.perf_counter() - t0
+        res = gathered_host.numpy()[rank * P: (rank + 1) * P]
+        h2d, d2h = world * P * 5 * 8, world * world * P * 22 * 8
+    te = max_over_ranks(te)
     e2e = slices_step * args.steps / te
     # inf losses are legitimate (moment explosion of E[S^1.75]: the reference returns inf there too)
     assert res.shape == (P, 22) and not np.isnan(res[:, 0]).any()
 
+    # value_noskip (a): the same step on a population where no grid point can be elided
+    Xs = torch.from_numpy(slow_decay_sets(min(P, 16384), skip=rank * P)).to(dev)
+    for _ in range(2):
+        pricer.normal_equations(Xs)
+    torch.cuda.synchronize(dev)
+    ms_slow = max_over_ranks(timed_steps(torch, dev, lambda: pricer.normal_equations(Xs), 2, flush) / 2)
+    noskip = {"slow_decay_population": {"value": world * Xs.shape[0] * N_MAT * 6 / (ms_slow * 1e-3),
+                                        "ms_per_step": ms_slow, "sets_per_gpu": int(Xs.shape[0]),
+                                        "what": "sigma in [1.5, 2], rho in [-0.99, -0.9], kappa theta tiny: |phi| never "
+                                                "decays on the grid, every point runs the full stage B and F"}}
+
+    # C4 (BASELINE.json config 4): 1,048,576 candidates of ONE population sharded over the ranks, objective +
+    # all-gather of the losses; strong scaling = this rate against world x the single-GPU objective rate of the
+    # same run; then the whole calibration (population + batched LM) on a surface the truth can price.
+    n_cand = args.c4_candidates
+    c4 = None
+    if n_cand > 0:
+        from pde_b200.calibration.population import sobol_population
+
+        Xc = torch.from_numpy(sobol_population(n_cand, LB, UB, seed=42)).to(dev)
+        obj = lambda Z: pricer.objective(Z)  # noqa: E731
+        sharded_map(obj, Xc[: 4096 * world])
+        barrier()
+        ms_c4 = max_over_ranks(timed_steps(torch, dev, lambda: sharded_map(obj, Xc), 2, flush) / 2)
+        n1 = min(n_cand, 131072)
+        pricer.objective(Xc[:n1])
+        torch.cuda.synchronize(dev)
+        ms_n1 = max_over_ranks(timed_steps(torch, dev, lambda: pricer.objective(Xc[:n1]), 2, flush) / 2)
+        rate_c4, rate_1 = n_cand * N_MAT / (ms_c4 * 1e-3), n1 * N_MAT / (ms_n1 * 1e-3)
+        c4 = {"candidates": n_cand, "objective_allgather_ms": ms_c4, "slices_per_s": rate_c4,
+              "single_gpu_objective_slices_per_s": rate_1, "strong_scaling_efficiency": rate_c4 / (world * rate_1),
+              "allgather_bytes": n_cand * 8}
+        if rank == 0 or world > 1:
+            import pandas as pd
+
+            from pde_b200.calibration import PopulationCalibrator
+
+            cal_pr = BatchPricer("fft", N_GRID, ETA, ALPHA, device=local)
+            Kc, Tc, mkc = feasible_surface(cal_pr)
+            df = pd.DataFrame({"strike": Kc, "maturity": Tc, "mid_price": mkc, "is_call": True})
+            cal = PopulationCalibrator(mode="fft", device=local)
+            cal.calibrate(df, S0, R, Q, n_candidates=4096 * world, n_starts=8, lm_iters=3)  # warm
+            barrier()
+            t0 = time.perf_counter()
+            r_ = cal.calibrate(df, S0, R, Q, n_candidates=n_cand, n_starts=32, lm_iters=30)
+            torch.cuda.synchronize(dev)
+            t_cal = max_over_ranks(time.perf_counter() - t0)
+            c4["calibration"] = {"seconds": t_cal, "rmse": float(r_.rmse), "n_options": int(Kc.size),
+                                 "params": [float(v) for v in r_.params.to_array()], "truth": TRUTH.tolist(),
+                                 "noise_rmse_expected": float(np.sqrt(np.mean((mkc * 0.001) ** 2))),
+                                 "best_population_loss": r_.convergence["best_population_loss"],
+                                 "surface": "32 x 50 grid minus the options whose fft price at the truth is below 0.05"}
+
     if rank == 0:
-        achieved = (P * N_MAT * 6 * FLOPS_PER_SLICE) / (ms / args.steps * 1e-3) / 1e12  # per GPU, TFLOP/s
+        per_launch_s = ms / args.steps * 1e-3
+        achieved = (P * N_MAT * 6 * FLOPS_PER_SLICE) / per_launch_s / 1e12  # per GPU, TFLOP/s, W1 convention
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
-        hbm_achieved = (P * N_MAT * 6 * BYTES_PER_SLICE) / (ms / args.steps * 1e-3) / 1e9
+        hbm_achieved = (P * N_MAT * 6 * BYTES_PER_SLICE) / per_launch_s / 1e9
+        cap = _ncu_capture(P)
+        executed = cap["executed_flop_per_launch"] / per_launch_s / 1e12 if cap else None
         line = {
             "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(P),
             "base_slices_per_s": value / 6.0,
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "slices/s", "h2d_bytes_per_step": int(world * P * 5 * 8),
-                    "d2h_bytes_per_step": int(world * P * 22 * 8)},
+            "e2e": {"value": e2e, "unit": "slices/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "path": "hb_normal_eq_host (C ABI, host buffers)" if world == 1 else
+                            "pinned H2D + hb_normal_eq + NCCL all-gather of the [P,22] rows + D2H of the gathered block"},
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
+            "significance_cut": {"log_cut": pricer.log_cut, "abs_price_error_budget": 2.0 ** -80},
+            "value_noskip": noskip,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(P),
-                         "fp64_pipe_active_ncu": ncu_pipe_active(P),
+                         "frac": achieved / peak,
+                         "frac_is": "W1 algorithmic flops (SURVEY.md 8d) / measured DFMA peak: exceeds 1 because shared "
+                                    "and elided work is not executed; frac_executed and fp64_pipe_active_ncu are the "
+                                    "utilisation figures",
+                         "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                         "executed_tflops": executed, "frac_executed": executed / peak if executed else None,
+                         "fp64_pipe_active_ncu": cap["fp64_pipe_active_pct"] / 100.0 if cap else None,
+                         "ncu_capture": ({"file": "profiles/r02_traffic.json", "kernel_source_hash": cap["kernel_source_hash"]}
+                                         if cap else "no capture of this kernel source: ncu-derived fields are null"),
                          "peak_source": "DFMA probe (hb_measure_fp64_peak) run in this process; "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_slice_W1": FLOPS_PER_SLICE,
                          "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak,
                                  "frac": hbm_achieved / hbm_peak, "bytes_per_slice": BYTES_PER_SLICE}},
         }
+        if shard_check is not None:
+            line["shard_check"] = shard_check
+        if c4 is not None:
+            line["c4"] = c4
         if world == 1 and not args.no_cpu:
+            noskip["noelide_build_exact_mode"] = noelide_rate(16384)
             rate, info = cpu_reference_rate(12.0)
             line["cpu_baseline"] = {"value": rate, "unit": "slices/s", "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"]}
@@ -356,7 +511,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sets", type=int, default=65536, help="parameter sets per GPU")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and no-elision legs")
+    ap.add_argument("--c4-candidates", type=int, default=1 << 20,
+                    help="candidates of the sharded population leg (BASELINE.json config 4); 0 skips it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -840,7 +840,7 @@ refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restri
     __shared__ JobState js;
     __shared__ double red[(NT / 32) * 23];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int V = (what >= W_NEQ) ? 6 : 1;
+    const int V = 1;  // W_PRICE / W_LOSS only (launch_jobs sends W_NEQ / W_JAC to refgrid_job6_kernel)
     const int n = S.n_opt, M = S.n_mat;
     const double du = 0.01;  // heston.cpp:127
     const int slices_per_set = V * M;
@@ -871,20 +871,34 @@ refgrid_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restri
             for (int v = 0; v < V; ++v)
                 for (int i = tid; i < S.n_intr; i += NT) rows[(size_t)v * n + S.intr_orig[i]] = S.intr_val[i];
         }
+        // Stage A and the Carr-Madan denominator depend on the grid point only (one variant per job here: the
+        // six-variant modes run refgrid_job6_kernel): once per job instead of once per maturity.
+        constexpr int PTS = kRefPoints / NT;
+        StageA ac[PTS];
+        cplx den[PTS];
+        {
+            const double* x = js.x[0];
+            const ClassConst cc = {x[0], x[2] * x[2], x[3] * x[2]};
+#pragma unroll 1
+            for (int k = 0; k < PTS; ++k) {
+                const double v = (double)(tid + k * NT) * du;
+                ac[k] = stage_a(cc, v, gc.ui);
+                den[k] = cm_inv_denominator(v, gc.alpha);
+            }
+        }
         for (int si = si_begin; si < si_end; ++si) {
             const int vnt = si / M, mat = si % M;
             const double* x = js.x[vnt];
-            const ClassConst cc = {x[0], x[2] * x[2], x[3] * x[2]};
+            const double s2 = x[2] * x[2];
             const double T = S.mat_T[mat];
-            const SliceConst sc = {x[0] * x[1] / cc.sigma2, x[4] / cc.sigma2, S.ln_spot + (S.rate - S.dividend) * T};
+            const SliceConst sc = {x[0] * x[1] / s2, x[4] / s2, S.ln_spot + (S.rate - S.dividend) * T};
 #pragma unroll 1
-            for (int j = tid; j < kRefPoints; j += NT) {
+            for (int k = 0; k < PTS; ++k) {  // ac[] / den[] indexed dynamically: thread-private local memory (L1)
+                const int j = tid + k * NT;
                 cplx r = {0.0, 0.0};  // integrand(0) == 0, heston.cpp:110
                 if (j > 0) {
-                    const double v = (double)j * du;
-                    const StageA a = stage_a(cc, v, gc.ui);
-                    const StageB b = stage_b(a, T);
-                    r = cmul(stage_f(b, sc, v, gc.ui), cm_inv_denominator(v, gc.alpha));
+                    const StageB b = stage_b(ac[k], T);
+                    r = cmul(stage_f(b, sc, (double)j * du, gc.ui), den[k]);
                 }
                 psi[j] = make_double2(r.re, r.im);
             }

@@ -35,6 +35,12 @@ def sharded_map(fn: Callable, X, group=None):
     P = X.shape[0]
     lo, hi = shard_bounds(P, rank, world)
     local = fn(X[lo:hi])
+    if P % world == 0:
+        # even partition (the usual case: populations are powers of two): gather straight into the result,
+        # no padding, no slicing, no concatenation
+        out = torch.empty((P,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     width = (P + world - 1) // world  # equal-size buckets for all_gather_into_tensor
     tail = tuple(local.shape[1:])
     padded = torch.zeros((width,) + tail, dtype=local.dtype, device=local.device)

@@ -106,7 +106,7 @@ def test_integration_binding_matches_ctypes_host_path():
                   [-1.0, 0.04, 0.3, -0.7, 0.04]])
     for mode in ("fft", "refgrid"):
         ours = BatchPricer(mode).set_surface(K, T, ic, None, S0=S0, r=R, q=Q)
-        mk = ours.price_host(X[:1])[0] * 1.01
+        mk = np.maximum(ours.price_host(X[:1])[0], 0.01) * 1.01
         ours.set_surface(K, T, ic, mk, S0=S0, r=R, q=Q)
         plan = q.heston.B200Plan(mode)
         plan.set_surface(K, T, ic.astype(np.uint8), mk, S0, R, Q)

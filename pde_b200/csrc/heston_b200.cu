@@ -520,19 +520,35 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     }
     std::sort(mats.begin(), mats.end());
     mats.erase(std::unique(mats.begin(), mats.end()), mats.end());
-    const int M = (int)mats.size();
-    std::vector<std::vector<int>> by_mat(M);
+    std::vector<std::vector<int>> by_mat(mats.size());
     for (int i = 0; i < n_opt; ++i) {
         const double K = strike[i], T = maturity[i];
         if (!(K > 0.0) || !(spot > 0.0) || !(T > 0.0)) continue;
         int m = (int)(std::lower_bound(mats.begin(), mats.end(), T) - mats.begin());
         by_mat[m].push_back(i);
     }
+    // The fused kernel's epilogue keeps one value per DISTINCT quoted bin of a maturity in shared memory (512 of
+    // them: 256 options can never need more): a longer maturity is priced as several slices of the same T.
+    {
+        constexpr size_t kMaxOptPerSlice = 256;
+        std::vector<double> mats2;
+        std::vector<std::vector<int>> by2;
+        for (size_t m = 0; m < mats.size(); ++m)
+            for (size_t a = 0; a < std::max<size_t>(by_mat[m].size(), 1); a += kMaxOptPerSlice) {
+                mats2.push_back(mats[m]);
+                by2.emplace_back(by_mat[m].begin() + std::min(a, by_mat[m].size()),
+                                 by_mat[m].begin() + std::min(a + kMaxOptPerSlice, by_mat[m].size()));
+            }
+        mats.swap(mats2);
+        by_mat.swap(by2);
+    }
+    const int M = (int)mats.size();
     std::vector<double> mat_disc(M), mat_fwd(M);
     std::vector<int> mat_off(M + 1, 0), opt_orig, opt_bin;
     std::vector<unsigned> need_mask(M, 0u);
     std::vector<double> opt_frac, opt_s0, opt_s1, opt_lnk, opt_kdisc;
     std::vector<uint8_t> opt_call;
+    std::vector<int> bin_off(M + 1, 0), bin_m, opt_b0, opt_b1;
     const int Nsub = pl->Nsub;
     double scale_max = 0.0;
     for (int m = 0; m < M; ++m) {
@@ -576,6 +592,32 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
             }
         }
         mat_off[m + 1] = (int)opt_orig.size();
+        // distinct quoted bins of this maturity (ascending) and each option's two indices into that list
+        if (pl->mode == HB_MODE_FFT) {
+            std::vector<int> bins;
+            for (int o = mat_off[m]; o < mat_off[m + 1]; ++o)
+                if (opt_bin[o] >= 0) {
+                    bins.push_back(opt_bin[o]);
+                    bins.push_back(opt_bin[o] + 1);
+                }
+            std::sort(bins.begin(), bins.end());
+            bins.erase(std::unique(bins.begin(), bins.end()), bins.end());
+            for (int o = mat_off[m]; o < mat_off[m + 1]; ++o) {
+                if (opt_bin[o] < 0) {
+                    opt_b0.push_back(-1);
+                    opt_b1.push_back(-1);
+                } else {
+                    const int i0 = (int)(std::lower_bound(bins.begin(), bins.end(), opt_bin[o]) - bins.begin());
+                    opt_b0.push_back(i0);
+                    opt_b1.push_back(i0 + 1);  // opt_bin + 1 follows opt_bin in the sorted distinct list
+                }
+            }
+            bin_m.insert(bin_m.end(), bins.begin(), bins.end());
+        } else {
+            opt_b0.resize(opt_orig.size(), -1);
+            opt_b1.resize(opt_orig.size(), -1);
+        }
+        bin_off[m + 1] = (int)bin_m.size();
     }
     std::vector<double> mkt(n_opt, nan);
     if (market) std::copy(market, market + n_opt, mkt.begin());
@@ -584,7 +626,8 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     const size_t o_T = bb.add(mats), o_disc = bb.add(mat_disc), o_fwd = bb.add(mat_fwd), o_moff = bb.add(mat_off),
                  o_orig = bb.add(opt_orig), o_bin = bb.add(opt_bin), o_frac = bb.add(opt_frac), o_s0 = bb.add(opt_s0),
                  o_s1 = bb.add(opt_s1), o_lnk = bb.add(opt_lnk), o_kd = bb.add(opt_kdisc), o_call = bb.add(opt_call),
-                 o_nm = bb.add(need_mask), o_io = bb.add(intr_orig), o_iv = bb.add(intr_val),
+                 o_nm = bb.add(need_mask), o_bo = bb.add(bin_off), o_bm = bb.add(bin_m), o_b0 = bb.add(opt_b0),
+                 o_b1 = bb.add(opt_b1), o_io = bb.add(intr_orig), o_iv = bb.add(intr_val),
                  o_mkt = bb.add(mkt);
     const size_t o_K = bb.add(std::vector<double>(strike, strike + n_opt)),
                  o_Tm = bb.add(std::vector<double>(maturity, maturity + n_opt)),
@@ -624,6 +667,10 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     S.opt_kdisc = (const double*)(base + o_kd);
     S.opt_call = (const uint8_t*)(base + o_call);
     S.need_mask = (const unsigned*)(base + o_nm);
+    S.bin_off = (const int*)(base + o_bo);
+    S.bin_m = (const int*)(base + o_bm);
+    S.opt_b0 = (const int*)(base + o_b0);
+    S.opt_b1 = (const int*)(base + o_b1);
     S.intr_orig = (const int*)(base + o_io);
     S.intr_val = (const double*)(base + o_iv);
     S.mkt_orig = (const double*)(base + o_mkt);

@@ -70,6 +70,12 @@ struct SurfaceDev {
     const double* opt_kdisc; // K exp(-r T) (put parity, heston.cpp:148)
     const uint8_t* opt_call;
     const unsigned* need_mask;  // [n_mat] FFT: digits m_{L-2} of the quoted bins (outputs kept by the S = 8 pass)
+    // FFT, bin-sum epilogue: the DISTINCT grid bins each maturity quotes (ascending) and, per option, the indices of
+    // its two bracketing bins in its maturity's list (-1: ln K is off the grid)
+    const int* bin_off;  // [n_mat+1]
+    const int* bin_m;    // [bin_off[n_mat]] full-grid bin index m
+    const int* opt_b0;   // [n_sorted]
+    const int* opt_b1;
     const int* intr_orig;    // options not priced through a slice (T == 0 or invalid)
     const double* intr_val;  // intrinsic value or NaN
     const double* mkt_orig;  // [n_opt] market prices in caller order (may be null for W_PRICE)
@@ -102,6 +108,7 @@ struct SubSlice {
     double T, kts, v0s, lsm, disc, fwd;
     int mat, variant;
     int o0, o1;  // options of this maturity: sorted indices [o0, o1)
+    int b0, nb;  // its distinct quoted bins: S.bin_m[b0 .. b0 + nb)
 };
 struct Group {
     ClassConst cc;
@@ -196,6 +203,8 @@ __device__ __forceinline__ void fill_group(Group& grp, const JobState& js, const
         s.o0 = S.mat_off[mat];
         s.o1 = S.mat_off[mat + 1];
         max_opt = max(max_opt, s.o1 - s.o0);
+        s.b0 = S.bin_off ? S.bin_off[mat] : 0;
+        s.nb = S.bin_off ? S.bin_off[mat + 1] - s.b0 : 0;
         grp.fmask[g] = S.need_mask ? S.need_mask[mat] : 0xffu;
     }
     grp.max_opt = max_opt;
@@ -426,11 +435,45 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     // K3 works on all slices of a group at once: TPG threads per slice, two threads per option (one per
     // bracketing bin).  The option's constants are loaded one step ahead (before the last FFT pass /
     // before the previous batch is finished) so their latency is off the critical path.
-    constexpr int TPG = (NT / kMaxGroup) & ~1;
+#ifndef HB_BINSUM
+#define HB_BINSUM 1
+#endif
     struct K3Opt {
         int o, bin, orig, call;
         double s0, s1, frac, kdisc;
     };
+#if HB_BINSUM
+    // K3': one thread per option; `bin` = index of the lower bracketing bin in the maturity's distinct-bin list,
+    // `call` = is_call | index of the upper one << 1
+    constexpr int kMaxBins = 512;  // distinct bins per maturity (hb_surface_set splits longer maturities)
+    __shared__ double s_xs[kMaxGroup][kMaxBins];
+    constexpr int TPG = NT / kMaxGroup;
+    const int k3_g = tid / TPG, k3_lt = tid - k3_g * TPG;
+    // (o0, o1): the option range of this thread's slice, copied out of the group descriptor by the caller -- the
+    // descriptor buffer may be refilled for group gi + 2 once the slices are released
+    auto k3_load = [&](int o0, int o1, int base) -> K3Opt {
+        K3Opt q;
+        q.o = -1;
+        q.bin = -1;
+        q.orig = q.call = 0;
+        q.s0 = q.s1 = q.frac = q.kdisc = 0.0;
+        {
+            const int o = o0 + base + k3_lt;
+            if (o < o1) {
+                q.o = o;
+                q.bin = S.opt_b0[o];
+                q.orig = S.opt_orig[o];
+                q.call = (int)S.opt_call[o] | (S.opt_b1[o] << 1);
+                q.s0 = S.opt_s0[o];
+                q.s1 = S.opt_s1[o];
+                q.frac = S.opt_frac[o];
+                q.kdisc = S.opt_kdisc[o];
+            }
+        }
+        return q;
+    };
+#else
+    constexpr int TPG = (NT / kMaxGroup) & ~1;
     const int k3_g = tid / TPG, k3_lt = tid - k3_g * TPG, k3_half = k3_lt & 1;
     auto k3_load = [&](const Group& grp, int base) -> K3Opt {
         K3Opt q;
@@ -455,6 +498,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
         }
         return q;
     };
+#endif
 
     for (long long job = blockIdx.x; job < n_jobs; job = next_job(job)) {
         const int p = split ? (int)(job / groups_per_set) : (int)job;
@@ -719,6 +763,111 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 // The S = 8 butterfly of thread 8 blk' + t' reads the slots 64 blk' + t' + 8 r', written in the
                 // S = 64 pass by the threads 64 (blk' >> 3) + t' + 8 r': both sit in the same 64-thread group, so
                 // this hand-over needs a barrier among two warps only (named barriers 1..8), not the whole CTA.
+#if HB_BINSUM
+            }
+            // ---- K3': the quoted bins straight from the S = 64 pass, interpolation, clamp, parity -> price rows ----
+            // After the passes down to stride 64 the 64 values that still have to be combined into X_m sit in ONE
+            // contiguous block (its base spells the resolved low digits of m) and X_m = sum_t z[t] W_64^{t mu},
+            // mu = m >> 3(L-2).  Carr-Madan quotes ~70 consecutive bins: eight lanes per DISTINCT bin each sum eight
+            // terms (w8 powers from the constant bank, one W_64 twiddle from the table) and a shuffle tree adds
+            // them -- no S = 8 pass, no masks, one CTA barrier less, a third of the FP64 work of that pass.
+            const int my_o0 = (k3_g < count) ? grp.s[k3_g].o0 : 0, my_o1 = (k3_g < count) ? grp.s[k3_g].o1 : 0;
+            K3Opt cur = k3_load(my_o0, my_o1, 0);
+            int it_m = -1;  // full-grid bin of this thread's item in the first round, loaded ahead of the barrier
+            {
+                const int it = tid >> 3;
+                int g = 0, i = it;
+#pragma unroll
+                for (int gg = 0; gg < kMaxGroup - 1; ++gg)
+                    if (g == gg && gg + 1 < count && i >= grp.s[gg].nb) {
+                        i -= grp.s[gg].nb;
+                        g = gg + 1;
+                    }
+                if (i < grp.s[g].nb) it_m = S.bin_m[grp.s[g].b0 + i];
+            }
+            HB_PROBE_T(pt4);
+            __syncthreads();  // every slice of the group has been through the S = 64 pass
+            HB_PROBE_T(pt5);
+            {
+                constexpr int L = Log8<N>::value;
+                int total = 0;
+                for (int g = 0; g < count; ++g) total += grp.s[g].nb;
+                const int part = tid & 7;
+#pragma unroll 1
+                for (int it0 = 0; it0 < total; it0 += NT / 8) {  // block-uniform trip count (shuffles inside)
+                    const int it = it0 + (tid >> 3);
+                    int g = 0, i = it;
+#pragma unroll
+                    for (int gg = 0; gg < kMaxGroup - 1; ++gg)
+                        if (g == gg && gg + 1 < count && i >= grp.s[gg].nb) {
+                            i -= grp.s[gg].nb;
+                            g = gg + 1;
+                        }
+                    const bool active = i < grp.s[g].nb;
+                    const int mfull = (it0 == 0) ? it_m : (active ? S.bin_m[grp.s[g].b0 + i] : 0);
+                    cplx y = {0.0, 0.0};
+                    if (active) {
+                        const int m = mfull & (N - 1);
+                        int base = 0;
+#pragma unroll
+                        for (int d = 0; d < L - 2; ++d) base |= ((m >> (3 * d)) & 7) << (3 * (L - 1 - d));
+                        const int mu = m >> (3 * (L - 2));
+                        const double2* sl = slices + (size_t)g * N;
+                        cplx acc = {0.0, 0.0};
+#pragma unroll
+                        for (int a = 0; a < 8; ++a) {
+                            const cplx v = lds_c(sl, base + 8 * a + part);
+                            const double wc = kW8c[(a * mu) & 7], ws = kW8s[(a * mu) & 7];
+                            acc.re = fma(v.re, wc, fma(-v.im, ws, acc.re));
+                            acc.im = fma(v.re, ws, fma(v.im, wc, acc.im));
+                        }
+                        const double2 w = tw512[512 + ((part * mu) & 63)];  // W_64^{part mu}
+                        y.re = fma(acc.re, w.x, -(acc.im * w.y));
+                        if (DECIM) y.im = fma(acc.re, w.y, acc.im * w.x);
+                    }
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        y.re += __shfl_xor_sync(0xffffffffu, y.re, o);
+                        if (DECIM) y.im += __shfl_xor_sync(0xffffffffu, y.im, o);
+                    }
+                    if (active && part == 0) {
+                        double x = y.re;
+                        if (DECIM) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
+                            double sn, cs;
+                            sincospi(-2.0 * (double)(((long long)ph * mfull) % gc.n_full) / (double)gc.n_full, &sn, &cs);
+                            x = y.re * cs - y.im * sn;
+                        }
+                        s_xs[g][i] = x;
+                    }
+                }
+            }
+            const int max_opt = grp.max_opt;
+            const int gg = (k3_g < count) ? k3_g : 0;
+            // copied out: after the barrier below the descriptor buffer may be refilled for group gi + 2
+            const double s_disc = grp.s[gg].disc, s_fwd = grp.s[gg].fwd;
+            const int s_variant = grp.s[gg].variant;
+            // The slices have been read for the last time: release them (and the threads without an option to
+            // finish) to the next group's K1 before the interpolation and the global stores.
+            __syncthreads();
+            HB_PROBE_T(pt6);
+            {
+                for (int base = 0; base < max_opt; base += TPG) {
+                    if (base > 0) cur = k3_load(my_o0, my_o1, base);
+                    if (cur.o >= 0) {
+                        double* dst = rows + (size_t)s_variant * n + cur.orig;
+                        double price = __longlong_as_double(0x7ff8000000000000LL);
+                        if (cur.bin >= 0) {
+                            const double c0 = cur.s0 * s_xs[gg][cur.bin];
+                            const double c1 = cur.s1 * s_xs[gg][cur.call >> 1];
+                            double call = s_disc * (c0 + (c1 - c0) * cur.frac);
+                            if (ph > 0) call += *dst;
+                            price = (ph == R - 1) ? finish_price(call, (cur.call & 1) != 0, s_fwd, cur.kdisc) : call;
+                        }
+                        *dst = price;
+                    }
+                }
+            }
+#else
                 if (N == 4096 && NT == 512)
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + (tid >> 6)) : "memory");
                 else
@@ -774,6 +923,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     cur = nxt;
                 }
             }
+#endif
             HB_PROBE_T(pt7);
             HB_PROBE_ADD(0, pt0, pt1);  // K1 (incl. group set-up of the next group by one thread)
             HB_PROBE_ADD(1, pt1, pt2);  // pass 1

@@ -117,8 +117,11 @@ def test_integration_binding_matches_ctypes_host_path():
         assert plan.greeks(X[:2]).shape == (2, K.size, 5)
         # the calibrator-side closures of INTEGRATION.md section 2
         loss = plan.objective(np.ascontiguousarray(X[:3]))
-        p = np.maximum(plan.prices(X[None, 0])[0], 1e-10)
-        assert loss[0] == pytest.approx(np.sum(((p - mk) / mk) ** 2), rel=1e-12)
+        p = plan.prices(X[None, 0])[0]
+        want = 1e10 if (np.isnan(p).any() or (p <= 0).any()) else np.sum(((p - mk) / mk) ** 2)  # :507-511
+        assert loss[0] == pytest.approx(want, rel=1e-12)
+        res = (np.maximum(p, 1e-10) - mk) / mk  # the residual closure of INTEGRATION.md section 2
+        assert plan.normal_equations(X[None, 0])[0, 1] == pytest.approx(res @ res, rel=1e-12)
     # error mapping of the snippet's chk(): call-order errors -> RuntimeError with the library's message
     bare = q.heston.B200Plan("fft")
     with pytest.raises(RuntimeError, match="hb_surface_set"):

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import logging
 from dataclasses import dataclass, field
-from datetime import date, datetime
+from datetime import date, datetime, timezone
 from enum import Enum
 from typing import Dict, List, Optional
 
@@ -56,6 +56,11 @@ class CalibrationConfig:
     rmse_alert_threshold: float = 0.05
 
 
+def _utcnow() -> datetime:
+    """Naive UTC timestamp, as the reference's datetime.utcnow() (orchestrator.py:88) without its deprecation."""
+    return datetime.now(timezone.utc).replace(tzinfo=None)
+
+
 @dataclass
 class CalibrationRunResult:
     """orchestrator.py:74-110"""
@@ -66,7 +71,7 @@ class CalibrationRunResult:
     heston_result: Optional[Dict] = None
     sabr_result: Optional[Dict] = None
     ou_results: Optional[Dict[str, Dict]] = None
-    start_time: datetime = field(default_factory=datetime.utcnow)
+    start_time: datetime = field(default_factory=lambda: _utcnow())
     end_time: Optional[datetime] = None
     total_time: float = 0.0
     errors: List[str] = field(default_factory=list)
@@ -96,7 +101,7 @@ class CalibrationOrchestrator:
     def run_daily_calibration(self, underlying: str, options_data=None, spreads_data: Optional[Dict[str, np.ndarray]] = None,
                               S0: float = 100.0, r: float = 0.05, q: float = 0.02,
                               calibration_date: Optional[date] = None) -> CalibrationRunResult:
-        start = datetime.utcnow()
+        start = _utcnow()
         result = CalibrationRunResult(run_date=calibration_date or date.today(), status=CalibrationStatus.RUNNING,
                                       underlying=underlying, start_time=start)
         heston_ok = sabr_ok = ou_ok = True
@@ -116,7 +121,7 @@ class CalibrationOrchestrator:
                 sabr_ok = False
         if self.config.ou_enabled and spreads_data:
             result.warnings.append("OU fitting is out of scope of this build: %d spread series ignored" % len(spreads_data))
-        result.end_time = datetime.utcnow()
+        result.end_time = _utcnow()
         result.total_time = (result.end_time - start).total_seconds()
         if heston_ok and sabr_ok and ou_ok:
             result.status = CalibrationStatus.SUCCESS
@@ -142,11 +147,14 @@ class CalibrationOrchestrator:
         return df[df["mid_price"] > 0]
 
     def _run_heston_calibration(self, underlying, options_data, S0, r, q) -> Dict:
+        # clean first (rows without a positive mid price never reach the calibrator), then cap and count: the
+        # minimum applies to what is actually calibrated on
+        options_data = self._heston_frame(options_data)
         if len(options_data) > self.config.heston_max_options:
             options_data = self._filter_options_for_heston(options_data, self.config.heston_max_options)
         if len(options_data) < self.config.heston_min_options:
             raise CalibrationError(f"Insufficient options: {len(options_data)} < {self.config.heston_min_options}")
-        res = self.heston_calibrator.calibrate(market_options=self._heston_frame(options_data), S0=S0, r=r, q=q,
+        res = self.heston_calibrator.calibrate(market_options=options_data, S0=S0, r=r, q=q,
                                                warm_start=self._last_heston_params.get(underlying),
                                                use_cached_on_failure=self.config.use_cached_on_failure,
                                                underlying=underlying)

@@ -164,6 +164,7 @@ class SABRCalibrator:
         maturities = sorted(market_options["T"].unique())
         n_options = len(market_options)
         Ks, Vs, Ws, Fs, Ts, guesses, skipped = [], [], [], [], [], [], []
+        fit_idx = []  # strikes each smile is FITTED on: the objective kernel stages at most 512 strikes of a smile
         for T in maturities:
             d = market_options[market_options["T"] == T]
             if len(d) < 3:  # the reference logs the CalibrationError and records rmse = inf (:470-472)
@@ -172,6 +173,10 @@ class SABRCalibrator:
             Ks.append(d["strike"].values.astype(np.float64))
             Vs.append(d["implied_vol"].values.astype(np.float64))
             Ws.append(d["weight"].values.astype(np.float64) if "weight" in d.columns else np.ones(len(d)))
+            # a longer smile is fitted on 512 strikes spread evenly over it (the reference has no such limit; its
+            # fit quality below is still measured on every strike)
+            fit_idx.append(np.arange(len(d)) if len(d) <= 512 else
+                           np.unique(np.round(np.linspace(0, len(d) - 1, 512)).astype(int)))
             Fs.append(F0 * np.exp((r - q) * T) if use_forward else F0)
             Ts.append(T)
             guesses.append(warm_start.get(T) if warm_start else None)
@@ -179,7 +184,8 @@ class SABRCalibrator:
         rmse_by_maturity: Dict[float, float] = {T: float("inf") for T in skipped}
         total_errors: List[float] = []
         if Ts:
-            x, _ = self._fit(Ks, Vs, Fs, Ts, Ws, guesses)
+            x, _ = self._fit([k[ix] for k, ix in zip(Ks, fit_idx)], [v[ix] for v, ix in zip(Vs, fit_idx)], Fs, Ts,
+                             [w[ix] for w, ix in zip(Ws, fit_idx)], guesses)
             eng = self._engine(self.beta)
             for i, T in enumerate(Ts):
                 model = eng.vols_host([x[i]], Ks[i], Fs[i], T, "py")[0]

@@ -773,71 +773,87 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             // them -- no S = 8 pass, no masks, one CTA barrier less, a third of the FP64 work of that pass.
             const int my_o0 = (k3_g < count) ? grp.s[k3_g].o0 : 0, my_o1 = (k3_g < count) ? grp.s[k3_g].o1 : 0;
             K3Opt cur = k3_load(my_o0, my_o1, 0);
-            int it_m = -1;  // full-grid bin of this thread's item in the first round, loaded ahead of the barrier
-            {
-                const int it = tid >> 3;
-                int g = 0, i = it;
-#pragma unroll
-                for (int gg = 0; gg < kMaxGroup - 1; ++gg)
-                    if (g == gg && gg + 1 < count && i >= grp.s[gg].nb) {
-                        i -= grp.s[gg].nb;
-                        g = gg + 1;
+            // item -> (slice, index in the slice's distinct-bin list): the bins of a group's slices numbered consecutively
+            int nb0 = grp.s[0].nb, nb1 = count > 1 ? grp.s[1].nb : 0, nb2 = count > 2 ? grp.s[2].nb : 0;
+            const int total = nb0 + nb1 + nb2;
+            auto item_at = [&](int it, int& g, int& i) -> bool {
+                g = 0;
+                i = it;
+                if (i >= nb0) {
+                    i -= nb0;
+                    g = 1;
+                    if (i >= nb1) {
+                        i -= nb1;
+                        g = 2;
                     }
-                if (i < grp.s[g].nb) it_m = S.bin_m[grp.s[g].b0 + i];
+                }
+                return it < total;
+            };
+            // full-grid bins of this thread's two items of the first round, loaded ahead of the barrier
+            int pre_m[2] = {0, 0};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                int g, i;
+                if (item_at((tid >> 3) + u * (NT / 8), g, i)) pre_m[u] = S.bin_m[grp.s[g].b0 + i];
             }
             HB_PROBE_T(pt4);
             __syncthreads();  // every slice of the group has been through the S = 64 pass
             HB_PROBE_T(pt5);
             {
                 constexpr int L = Log8<N>::value;
-                int total = 0;
-                for (int g = 0; g < count; ++g) total += grp.s[g].nb;
                 const int part = tid & 7;
+                // two items per thread and round: their load -> FMA -> shuffle chains overlap
 #pragma unroll 1
-                for (int it0 = 0; it0 < total; it0 += NT / 8) {  // block-uniform trip count (shuffles inside)
-                    const int it = it0 + (tid >> 3);
-                    int g = 0, i = it;
+                for (int it0 = 0; it0 < total; it0 += 2 * (NT / 8)) {  // block-uniform trip count (shuffles inside)
+                    cplx y[2] = {{0.0, 0.0}, {0.0, 0.0}};
+                    int gs[2], is[2], ms[2];
+                    bool act[2];
 #pragma unroll
-                    for (int gg = 0; gg < kMaxGroup - 1; ++gg)
-                        if (g == gg && gg + 1 < count && i >= grp.s[gg].nb) {
-                            i -= grp.s[gg].nb;
-                            g = gg + 1;
+                    for (int u = 0; u < 2; ++u) {
+                        act[u] = item_at(it0 + (tid >> 3) + u * (NT / 8), gs[u], is[u]);
+                        ms[u] = (it0 == 0) ? pre_m[u] : (act[u] ? S.bin_m[grp.s[gs[u]].b0 + is[u]] : 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (act[u]) {
+                            const int m = ms[u] & (N - 1);
+                            int base = 0;
+#pragma unroll
+                            for (int d = 0; d < L - 2; ++d) base |= ((m >> (3 * d)) & 7) << (3 * (L - 1 - d));
+                            const int mu = m >> (3 * (L - 2));
+                            const double2* sl = slices + (size_t)gs[u] * N;
+                            cplx acc = {0.0, 0.0};
+#pragma unroll
+                            for (int a = 0; a < 8; ++a) {
+                                const cplx v = lds_c(sl, base + 8 * a + part);
+                                const double wc = kW8c[(a * mu) & 7], ws = kW8s[(a * mu) & 7];
+                                acc.re = fma(v.re, wc, fma(-v.im, ws, acc.re));
+                                acc.im = fma(v.re, ws, fma(v.im, wc, acc.im));
+                            }
+                            const double2 w = tw512[512 + ((part * mu) & 63)];  // W_64^{part mu}
+                            y[u].re = fma(acc.re, w.x, -(acc.im * w.y));
+                            if (DECIM) y[u].im = fma(acc.re, w.y, acc.im * w.x);
                         }
-                    const bool active = i < grp.s[g].nb;
-                    const int mfull = (it0 == 0) ? it_m : (active ? S.bin_m[grp.s[g].b0 + i] : 0);
-                    cplx y = {0.0, 0.0};
-                    if (active) {
-                        const int m = mfull & (N - 1);
-                        int base = 0;
-#pragma unroll
-                        for (int d = 0; d < L - 2; ++d) base |= ((m >> (3 * d)) & 7) << (3 * (L - 1 - d));
-                        const int mu = m >> (3 * (L - 2));
-                        const double2* sl = slices + (size_t)g * N;
-                        cplx acc = {0.0, 0.0};
-#pragma unroll
-                        for (int a = 0; a < 8; ++a) {
-                            const cplx v = lds_c(sl, base + 8 * a + part);
-                            const double wc = kW8c[(a * mu) & 7], ws = kW8s[(a * mu) & 7];
-                            acc.re = fma(v.re, wc, fma(-v.im, ws, acc.re));
-                            acc.im = fma(v.re, ws, fma(v.im, wc, acc.im));
-                        }
-                        const double2 w = tw512[512 + ((part * mu) & 63)];  // W_64^{part mu}
-                        y.re = fma(acc.re, w.x, -(acc.im * w.y));
-                        if (DECIM) y.im = fma(acc.re, w.y, acc.im * w.x);
                     }
 #pragma unroll
                     for (int o = 1; o < 8; o <<= 1) {
-                        y.re += __shfl_xor_sync(0xffffffffu, y.re, o);
-                        if (DECIM) y.im += __shfl_xor_sync(0xffffffffu, y.im, o);
-                    }
-                    if (active && part == 0) {
-                        double x = y.re;
-                        if (DECIM) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
-                            double sn, cs;
-                            sincospi(-2.0 * (double)(((long long)ph * mfull) % gc.n_full) / (double)gc.n_full, &sn, &cs);
-                            x = y.re * cs - y.im * sn;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            y[u].re += __shfl_xor_sync(0xffffffffu, y[u].re, o);
+                            if (DECIM) y[u].im += __shfl_xor_sync(0xffffffffu, y[u].im, o);
                         }
-                        s_xs[g][i] = x;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (act[u] && part == 0) {
+                            double x = y[u].re;
+                            if (DECIM) {  // Re(W_N^{ph m} Y[m mod Nsub]); exact angle reduction in integers
+                                double sn, cs;
+                                sincospi(-2.0 * (double)(((long long)ph * ms[u]) % gc.n_full) / (double)gc.n_full, &sn, &cs);
+                                x = y[u].re * cs - y[u].im * sn;
+                            }
+                            s_xs[gs[u]][is[u]] = x;
+                        }
                     }
                 }
             }

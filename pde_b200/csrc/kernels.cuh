@@ -18,10 +18,13 @@
 //   classes kappa+h, sigma+h, rho+h: own stage A, shared by the 3 maturities of a group.
 // A group = up to 3 slices that are resident in shared memory at once (3 x 64 KiB at
 // N = 4096).  Arithmetic of a perturbed slice is identical to evaluating it on its own.
-// Work that is provably without effect is not executed (bit-identical output):
-// stage A is cached per (set, class) in thread-private local memory; stage F skips the cexp when
-// exp underflows to exactly 0; the perturbed classes skip stage B/F where the base set's integrand
-// has decayed with a wide margin; CTAs pull jobs from a global counter because jobs then differ in cost.
+// Work without effect is not executed: stage A is cached per (set, class) in thread-private
+// local memory; stage F skips the cexp where |phi| is below the plan's significance cut (exactly 0 below exp's
+// underflow; GridConst::cut bounds what all dropped points together can add to a price); the perturbed classes
+// skip stage B/F where the base set's integrand lies 54 units of log|phi| below that cut -- a MEASURED margin
+// (condition number of the exponent < 200 over the calibrator's default box, tests/test_host_math.py), so that
+// skip is switched off for any other box (hb_set_bounds); the first two transform passes skip rows that are exact
+// zeros; CTAs pull jobs from a global counter because jobs then differ in cost.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -31,6 +31,8 @@ FP64 = {"DFMA", "DADD", "DMUL", "DSETP", "MUFU"}
 MEM = {"LDS", "STS", "LDG", "STG", "LDL", "STL", "LDC", "LDCU", "ATOMS", "ATOMG", "RED", "UBLKCP", "SYNCS"}
 for k, h in hist.items():
     tot = sum(h.values())
+    if tot == 0:
+        continue
     f = sum(v for o, v in h.items() if o in FP64)
     mm = sum(v for o, v in h.items() if o in MEM)
     print(f"\n## {k}: {tot} SASS instructions, FP64 {100 * f / tot:.1f} %, memory {100 * mm / tot:.1f} %"

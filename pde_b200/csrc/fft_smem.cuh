@@ -28,6 +28,16 @@
 
 namespace hb {
 
+// Index checks of the diagnostic build (-DHB_CHECK; compute-sanitizer is closed on the GPU pool): every slice access
+// of the fused kernel's transform / epilogue and every table index is asserted; the whole GPU test-suite runs over
+// that build once per round (PDE_B200_LIB=...libheston_b200_check.so).  Compiled out of the product library.
+#ifdef HB_CHECK
+#include <assert.h>
+#define HB_ASSERT(cond) assert(cond)
+#else
+#define HB_ASSERT(cond)
+#endif
+
 __device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 7); }
 
 __device__ __forceinline__ cplx lds_c(const double2* s, int i) {
@@ -308,6 +318,7 @@ __device__ __forceinline__ void dif_pass_first(double2* base, int count, const d
         const unsigned lm = (live >> (8 * g)) & 0xffu;
         if (lm == 0u) continue;
         double2* sl = base + (size_t)g * N;
+        HB_ASSERT(tid >= 0 && tid + 7 * S < N);
         if (lm == 1u) {
             const cplx v0 = lds_c(sl, tid);
 #pragma unroll
@@ -342,6 +353,7 @@ __device__ __forceinline__ void dif_pass_second(double2* base, int count, const 
 #pragma unroll
     for (int g = 0; g < kMaxGroupFft; ++g) {
         const int J = (g < count) ? jlive[g] : 0;
+        HB_ASSERT(J >= 0 && J <= N && p0 >= 0 && p0 + 7 * S < N);
         nr[g] = (J > N / 8) ? 8 : max(0, min(8, (J - t + S - 1) / S));
         any |= nr[g];
     }

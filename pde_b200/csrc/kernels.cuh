@@ -637,6 +637,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                 }
 #pragma unroll 1
                 for (int k = 0, j0 = tid; j0 < N; ++k, j0 += NT) {
+                    HB_ASSERT(k < 8 && count >= 1 && count <= gmax && gmax <= kMaxGroup);
                     const int j = ph + R * j0;  // index on the full N-point grid
                     const double v = gc.eta * (double)j;
                     const int kn = (k + 1 < PTS) ? k + 1 : k;
@@ -825,6 +826,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                             for (int d = 0; d < L - 2; ++d) base |= ((m >> (3 * d)) & 7) << (3 * (L - 1 - d));
                             const int mu = m >> (3 * (L - 2));
                             const double2* sl = slices + (size_t)gs[u] * N;
+                            HB_ASSERT(gs[u] >= 0 && gs[u] < count && is[u] >= 0 && is[u] < kMaxBins && base >= 0 &&
+                                      base + 63 < N && mu >= 0 && mu < 64);
                             cplx acc = {0.0, 0.0};
 #pragma unroll
                             for (int a = 0; a < 8; ++a) {
@@ -865,6 +868,9 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
             // copied out: after the barrier below the descriptor buffer may be refilled for group gi + 2
             const double s_disc = grp.s[gg].disc, s_fwd = grp.s[gg].fwd;
             const int s_variant = grp.s[gg].variant;
+#ifdef HB_CHECK
+            const int grp_nb = grp.s[gg].nb;
+#endif
             // The slices have been read for the last time: release them (and the threads without an option to
             // finish) to the next group's K1 before the interpolation and the global stores.
             __syncthreads();
@@ -875,7 +881,10 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                     if (cur.o >= 0) {
                         double* dst = rows + (size_t)s_variant * n + cur.orig;
                         double price = __longlong_as_double(0x7ff8000000000000LL);
+                        HB_ASSERT(cur.orig >= 0 && cur.orig < n && s_variant >= 0 && s_variant < 6);
                         if (cur.bin >= 0) {
+                            HB_ASSERT(cur.bin < kMaxBins && (cur.call >> 1) >= 0 && (cur.call >> 1) < kMaxBins &&
+                                      cur.bin < grp_nb && (cur.call >> 1) < grp_nb);
                             const double c0 = cur.s0 * s_xs[gg][cur.bin];
                             const double c1 = cur.s1 * s_xs[gg][cur.call >> 1];
                             double call = s_disc * (c0 + (c1 - c0) * cur.frac);

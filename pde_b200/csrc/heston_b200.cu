@@ -11,12 +11,14 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
 #include <string>
 #include <vector>
 
+#include "direct_kernel.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -105,6 +107,10 @@ struct hb_plan {
     bool tail_ok = true;                       // FD bounds inside the validated default box
     cudaEvent_t last_launch = nullptr;         // recorded after every launch of this plan (hb_surface_set waits on it)
     std::vector<double> scalar_key;            // hb_model_* cache: the surface this plan currently holds
+    // direct-sum kernel (direct_kernel.cuh): grid tables (per plan), pair lists (per surface), stage-A cache
+    Arena dtab, acache, route;
+    DirectDev D{};
+    bool direct_ok = false;  // surface fits the direct kernel's limits (pairs per maturity, maturities)
     const double* d_strike = nullptr;    // caller-order copies for the implied-vol epilogue
     const double* d_maturity = nullptr;
     const uint8_t* d_is_call = nullptr;
@@ -143,6 +149,21 @@ template <typename K>
 int set_smem(K kernel, size_t bytes) {
     HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return HB_OK;
+}
+
+// The direct-sum kernel pays per live grid point: it takes the plans with a significance cut (exact mode, cut = -746,
+// keeps thousands of points per slice and stays on the transform kernel).  HB_DIRECT=0 forces the transform kernel
+// (A/B measurements, parity of one against the other).
+constexpr double kDirectMinCut = -120.0;
+bool direct_enabled() {
+    const char* e = std::getenv("HB_DIRECT");
+    return !(e && e[0] == '0');
+}
+// Mean prefix length (grid points per maturity) above which a parameter set is priced by the transform kernel:
+// measured crossover of the two kernels on B200.  HB_DIRECT_THR=0 switches the routing off.
+int direct_threshold() {
+    const char* e = std::getenv("HB_DIRECT_THR");
+    return e ? std::atoi(e) : 1000;
 }
 
 int gmax_for(int N) { return (N == 4096 || N == 512) ? 3 : 1; }
@@ -186,31 +207,36 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
     const size_t row_bytes = (size_t)6 * std::max(n, 1) * sizeof(double);
     // dynamic job queue: one counter per plan, reset in stream order before each launch
     {
-        int rc = pl->ctr.reserve(sizeof(unsigned long long));
+        int rc = pl->ctr.reserve(2 * sizeof(unsigned long long));  // [1]: the transform kernel of a routed launch
         if (rc) return rc;
-        HB_CUDA(cudaMemsetAsync(pl->ctr.dev, 0, sizeof(unsigned long long), st));
+        HB_CUDA(cudaMemsetAsync(pl->ctr.dev, 0, 2 * sizeof(unsigned long long), st));
     }
     unsigned long long* ctr = (unsigned long long*)pl->ctr.dev;
 
-    if (pl->mode == HB_MODE_FFT) {
+    // Transform kernel (fft_job_kernel).  job_ids / p_count (device): the sets a routed launch leaves to it.
+    // split_mode: -1 = by batch size, 0 / 1 = as the routed launch decided; finalize: run the finalize kernel of a split launch
+    auto launch_fft = [&](const int* job_ids, const int* p_count, unsigned long long* counter, size_t scratch_off,
+                          int split_mode, bool finalize) -> int {
         const int gmax = gmax_for(pl->Nsub);
         const int g0 = ((V > 1 ? 3 * M : M) + gmax - 1) / gmax, g1 = (M + gmax - 1) / gmax;
         const int groups = g0 + (V > 1 ? 3 : 0) * g1;
         const int max_ctas = pl->sm_count;
         // small batches: one job per (set, group) so every SM has work
-        const bool split = groups > 0 && (long long)P < 2LL * max_ctas && (size_t)P * row_bytes <= (size_t(1) << 30);
+        const bool split = split_mode >= 0 ? split_mode != 0
+                                           : groups > 0 && (long long)P < 2LL * max_ctas &&
+                                                 (size_t)P * row_bytes <= (size_t(1) << 30);
         const long long n_jobs = split ? (long long)P * groups : (long long)P;
         const int grid = (int)std::max<long long>(1, std::min<long long>(n_jobs, max_ctas));
         double* scratch = nullptr;
         if (what != W_PRICE) {
-            int rc = pl->scratch.reserve((size_t)(split ? P : grid) * row_bytes);
+            int rc = pl->scratch.reserve(scratch_off + (size_t)(split ? P : grid) * row_bytes);
             if (rc) return rc;
-            scratch = (double*)pl->scratch.dev;
+            scratch = (double*)((unsigned char*)pl->scratch.dev + scratch_off);
         }
         const size_t smem = job_smem_bytes(pl->Nsub, gmax);
 #define HB_LAUNCH_JOB(NN, NTT, DEC, ONE)                                                                       \
     fft_job_kernel<NN, NTT, DEC, ONE><<<grid, NTT, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, \
-                                                               scratch, gmax, split ? 1 : 0, ctr)
+                                                               scratch, gmax, split ? 1 : 0, counter, job_ids, p_count)
         const bool one = (V == 1);
         if (pl->Nsub == 4096) {
             if (pl->R == 1) {
@@ -227,7 +253,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
 #undef HB_LAUNCH_JOB
         g_launches++;
         HB_CUDA(cudaGetLastError());
-        if (split && what != W_PRICE) {
+        if (split && finalize && what != W_PRICE) {
             // same block size as the job kernel: the in-kernel finalize and this one then reduce in the
             // same order, so split and persistent launches agree bit for bit
             if (pl->Nsub == 4096)
@@ -240,7 +266,105 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             HB_CUDA(cudaGetLastError());
         }
         return HB_OK;
+    };
+    if (pl->mode == HB_MODE_FFT && direct_enabled() && pl->direct_ok && gc.cut >= kDirectMinCut) {
+        // Live prefix + direct sums (direct_kernel.cuh).  Small batches are cut into pieces of maturities so that
+        // every SM has work; the arithmetic of a maturity does not depend on the piece or wave it is priced in.
+        const int max_ctas = pl->sm_count;
+        const bool one = (V == 1);
+        const bool groups_ok = M > 0;
+        int pieces = 1;
+        if (M > 1 && (long long)P < 2LL * max_ctas && (size_t)P * row_bytes <= (size_t(1) << 30))
+            pieces = (int)std::min<long long>(M, (2LL * max_ctas + P - 1) / P);
+        const long long n_jobs = (long long)P * pieces;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(n_jobs, max_ctas));
+        double* scratch = nullptr;
+        if (what != W_PRICE) {
+            // persistent launches: per-CTA rows, twice (the transform kernel of a routed launch takes the second half:
+            // reserved here, in one piece, so that no pointer handed to a kernel is ever reallocated)
+            int rc = pl->scratch.reserve((size_t)(pieces > 1 ? P : 2 * grid) * row_bytes);
+            if (rc) return rc;
+            scratch = (double*)pl->scratch.dev;
+        }
+        {
+            int rc = pl->acache.reserve((size_t)grid * (one ? 1 : 4) * kDAFields * pl->N * sizeof(double2));
+            if (rc) return rc;
+        }
+        DirectDev D = pl->D;
+        D.acache = (double2*)pl->acache.dev;
+        D.job_ids = nullptr;
+        D.jtab = nullptr;
+        D.p_count = nullptr;
+        int rc;
+        // Routing (large batches): prefix lengths of every set first; sets whose mean prefix exceeds the threshold go
+        // to the transform kernel (second launch below), the rest to the direct kernel with their prefix table.
+        // Small batches (pieces > 1) are routed the same way, so that a set is priced by the same kernel whatever the
+        // batch it arrives in (bit-identical results); both kernels then leave their rows to one finalize launch.
+        const bool routed = direct_threshold() > 0 && pl->Nsub == 4096 && groups_ok;
+        int* counts = nullptr;
+        int* long_ids = nullptr;
+        if (routed) {
+            const size_t ids_off = 256, jt_off = ids_off + (((size_t)2 * P * sizeof(int) + 255) & ~size_t(255));
+            if ((rc = pl->route.reserve(jt_off + (size_t)P * std::max(M, 1) * sizeof(int)))) return rc;
+            unsigned char* rb = (unsigned char*)pl->route.dev;
+            counts = (int*)rb;
+            int* short_ids = (int*)(rb + ids_off);
+            long_ids = short_ids + P;
+            int* jtab = (int*)(rb + jt_off);
+            HB_CUDA(cudaMemsetAsync(counts, 0, 256, st));
+            const size_t ssm = (size_t)kScanWarps * D.nblk * sizeof(PrefixBlock);
+            const int sgrid = std::min((P + kScanWarps - 1) / kScanWarps, 8 * max_ctas);
+            if (one) {
+                if ((rc = set_smem(prefix_scan_kernel<true>, ssm))) return rc;
+                prefix_scan_kernel<true><<<sgrid, 32 * kScanWarps, ssm, st>>>(S, D, gc, pl->bd, d_params, ld, P, jtab,
+                                                                              direct_threshold(), short_ids, long_ids, counts);
+            } else {
+                if ((rc = set_smem(prefix_scan_kernel<false>, ssm))) return rc;
+                prefix_scan_kernel<false><<<sgrid, 32 * kScanWarps, ssm, st>>>(S, D, gc, pl->bd, d_params, ld, P, jtab,
+                                                                               direct_threshold(), short_ids, long_ids, counts);
+            }
+            g_launches++;
+            HB_CUDA(cudaGetLastError());
+            D.job_ids = short_ids;
+            D.jtab = jtab;
+            D.p_count = counts;
+        }
+        if (one) {
+            if ((rc = set_smem(direct_job_kernel<true>, DirectCfg<true>::smem_bytes()))) return rc;
+            direct_job_kernel<true><<<grid, kDNT, DirectCfg<true>::smem_bytes(), st>>>(
+                S, D, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, pieces, ctr);
+        } else {
+            if ((rc = set_smem(direct_job_kernel<false>, DirectCfg<false>::smem_bytes()))) return rc;
+            direct_job_kernel<false><<<grid, kDNT, DirectCfg<false>::smem_bytes(), st>>>(
+                S, D, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, pieces, ctr);
+        }
+        if (routed) {
+            g_launches++;
+            HB_CUDA(cudaGetLastError());
+            // the long-prefix sets, on the transform kernel (its own job counter; its own scratch rows unless both
+            // kernels write whole-batch rows for the common finalize)
+            if ((rc = launch_fft(long_ids, counts + 1, ctr + 1, pieces > 1 ? 0 : (size_t)grid * row_bytes,
+                                 pieces > 1 ? 1 : 0, false)))
+                return rc;
+            if (pieces > 1 && what != W_PRICE) {
+                finalize_rows_kernel<kDNT><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
+                                                                                       scratch, d_out, d_out2);
+                g_launches++;
+                HB_CUDA(cudaGetLastError());
+            }
+            return HB_OK;
+        }
+        g_launches++;
+        HB_CUDA(cudaGetLastError());
+        if (pieces > 1 && what != W_PRICE) {
+            finalize_rows_kernel<kDNT><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
+                                                                                   scratch, d_out, d_out2);
+            g_launches++;
+            HB_CUDA(cudaGetLastError());
+        }
+        return HB_OK;
     }
+    if (pl->mode == HB_MODE_FFT) return launch_fft(nullptr, nullptr, ctr, 0, -1, true);
     // REFGRID
     {
         const int slices = V * M;
@@ -420,8 +544,43 @@ int hb_plan_create(int mode, int n_grid, double eta, double alpha, int device, h
             rc = set_smem(fft_job_kernel<512, kNT512, false, true>, job_smem_bytes(512, gmax_for(512)));
             if (!rc) rc = set_smem(fft_job_kernel<512, kNT512, false, false>, job_smem_bytes(512, gmax_for(512)));
         }
+        // tables of the direct-sum kernel: twiddles (cos, sin)(pi k/N), k < 2N; Carr-Madan weights
+        // w_j e^{i b v_j}/(alpha^2 + alpha - v_j^2 + i (2 alpha + 1) v_j) (heston.cpp:117);
+        // block boundaries of the prefix bound
+        if (!rc) {
+            const int N = n_grid;
+            std::vector<double> tw((size_t)4 * N), tab((size_t)2 * N);
+            const long double pi_l = 3.14159265358979323846264338327950288L;
+            for (int k = 0; k < 2 * N; ++k) {
+                const long double a = pi_l * (long double)k / (long double)N;
+                tw[2 * (size_t)k] = (double)cosl(a);
+                tw[2 * (size_t)k + 1] = (double)sinl(a);
+            }
+            for (int j = 0; j < N; ++j) {
+                const double v = eta * (double)j, a = alpha * alpha + alpha - v * v, b = (2.0 * alpha + 1.0) * v;
+                const double wgt = (eta / 3.0) * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
+                const double r = wgt / (a * a + b * b);
+                tab[2 * (size_t)j] = a * r;
+                tab[2 * (size_t)j + 1] = -b * r;
+            }
+            std::vector<int> blk(kMaxPrefixBlocks + 1, 0);
+            const int nblk = prefix_blocks_host(N, blk.data());
+            BlobBuilder bb;
+            const size_t o_tw = bb.add(tw), o_tab = bb.add(tab), o_blk = bb.add(blk);
+            rc = pl->dtab.reserve(bb.bytes.size());
+            if (!rc && cudaMemcpy(pl->dtab.dev, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+                rc = fail(HB_ERR_CUDA, "upload of the direct-sum tables failed");
+            if (!rc) {
+                const unsigned char* base = (const unsigned char*)pl->dtab.dev;
+                pl->D.tw = (const double2*)(base + o_tw);
+                pl->D.tab = (const double2*)(base + o_tab);
+                pl->D.blk = (const int*)(base + o_blk);
+                pl->D.nblk = nblk;
+                pl->D.n_full = N;
+            }
+        }
         if (rc) {
-            delete pl;
+            hb_plan_destroy(pl);
             return rc;
         }
     }
@@ -444,6 +603,9 @@ int hb_plan_destroy(hb_plan* pl) {
     pl->surf.release();
     pl->scratch.release();
     pl->ctr.release();
+    pl->dtab.release();
+    pl->acache.release();
+    pl->route.release();
     pl->io_in.release();
     pl->io_out.release();
     pl->io_out2.release();
@@ -549,6 +711,9 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     std::vector<double> opt_frac, opt_s0, opt_s1, opt_lnk, opt_kdisc;
     std::vector<uint8_t> opt_call;
     std::vector<int> bin_off(M + 1, 0), bin_m, opt_b0, opt_b1;
+    // direct-sum kernel: the bins of a maturity as conjugate pairs around their centre (direct_kernel.cuh)
+    std::vector<int> mat_c2(M, 0), pair_off(M + 1, 0), pair_d2, opt_pq0, opt_pq1;
+    int max_pairs = 0;
     const int Nsub = pl->Nsub;
     double scale_max = 0.0;
     for (int m = 0; m < M; ++m) {
@@ -613,11 +778,32 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                 }
             }
             bin_m.insert(bin_m.end(), bins.begin(), bins.end());
+            // bin m = (c2 + s d2)/2, s = +-1: X_m = P(d2) + s Q(d2)
+            std::vector<int> d2s;
+            const int c2 = bins.empty() ? 0 : bins.front() + bins.back();
+            mat_c2[m] = c2;
+            for (int bm : bins) d2s.push_back(std::abs(2 * bm - c2));
+            std::sort(d2s.begin(), d2s.end());
+            d2s.erase(std::unique(d2s.begin(), d2s.end()), d2s.end());
+            auto pq_of = [&](int bm) {
+                const int d2 = std::abs(2 * bm - c2);
+                const int idx = (int)(std::lower_bound(d2s.begin(), d2s.end(), d2) - d2s.begin());
+                return (idx << 1) | (2 * bm - c2 >= 0 ? 1 : 0);
+            };
+            for (int o = mat_off[m]; o < mat_off[m + 1]; ++o) {
+                opt_pq0.push_back(opt_bin[o] < 0 ? -1 : pq_of(opt_bin[o]));
+                opt_pq1.push_back(opt_bin[o] < 0 ? -1 : pq_of(opt_bin[o] + 1));
+            }
+            pair_d2.insert(pair_d2.end(), d2s.begin(), d2s.end());
+            max_pairs = std::max(max_pairs, (int)d2s.size());
         } else {
             opt_b0.resize(opt_orig.size(), -1);
             opt_b1.resize(opt_orig.size(), -1);
+            opt_pq0.resize(opt_orig.size(), -1);
+            opt_pq1.resize(opt_orig.size(), -1);
         }
         bin_off[m + 1] = (int)bin_m.size();
+        pair_off[m + 1] = (int)pair_d2.size();
     }
     std::vector<double> mkt(n_opt, nan);
     if (market) std::copy(market, market + n_opt, mkt.begin());
@@ -632,9 +818,12 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     const size_t o_K = bb.add(std::vector<double>(strike, strike + n_opt)),
                  o_Tm = bb.add(std::vector<double>(maturity, maturity + n_opt)),
                  o_ic = bb.add(std::vector<uint8_t>(is_call, is_call + n_opt));
+    const size_t o_c2 = bb.add(mat_c2), o_po = bb.add(pair_off), o_pd = bb.add(pair_d2), o_q0 = bb.add(opt_pq0),
+                 o_q1 = bb.add(opt_pq1);
     pl->surf.want_pinned = true;
     // reserve() may free the old blob before a failing allocation: the plan holds no surface until the upload is done
     pl->has_surface = pl->has_market = false;
+    pl->direct_ok = false;
     pl->S = SurfaceDev{};
     pl->d_strike = pl->d_maturity = nullptr;
     pl->d_is_call = nullptr;
@@ -674,6 +863,12 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     S.intr_orig = (const int*)(base + o_io);
     S.intr_val = (const double*)(base + o_iv);
     S.mkt_orig = (const double*)(base + o_mkt);
+    pl->D.mat_c2 = (const int*)(base + o_c2);
+    pl->D.pair_off = (const int*)(base + o_po);
+    pl->D.pair_d2 = (const int*)(base + o_pd);
+    pl->D.opt_pq0 = (const int*)(base + o_q0);
+    pl->D.opt_pq1 = (const int*)(base + o_q1);
+    pl->direct_ok = pl->mode == HB_MODE_FFT && max_pairs <= kDMaxPairs && M <= kDMaxMat;
     pl->d_strike = (const double*)(base + o_K);
     pl->d_maturity = (const double*)(base + o_Tm);
     pl->d_is_call = (const uint8_t*)(base + o_ic);

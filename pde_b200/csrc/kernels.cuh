@@ -360,7 +360,11 @@ template <int N, int NT, bool DECIM, bool ONEVAR>
 __global__ void __launch_bounds__(NT, 1)
 fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
                double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int gmax,
-               int split, unsigned long long* job_counter) {
+               int split, unsigned long long* job_counter, const int* __restrict__ job_ids = nullptr,
+               const int* __restrict__ p_count = nullptr) {
+    // job_ids / p_count: the parameter sets routed to this kernel by prefix_scan_kernel (direct_kernel.cuh) and
+    // their number, both on the device; null = all P sets in order
+    if (p_count) P = *p_count;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* slices = reinterpret_cast<double2*>(smem_raw);
     double2* tw = slices + (size_t)gmax * N;
@@ -504,7 +508,8 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
 #endif
 
     for (long long job = blockIdx.x; job < n_jobs; job = next_job(job)) {
-        const int p = split ? (int)(job / groups_per_set) : (int)job;
+        const int pj = split ? (int)(job / groups_per_set) : (int)job;
+        const int p = job_ids ? job_ids[pj] : pj;
         const int gi_begin = split ? (int)(job % groups_per_set) : 0;
         const int gi_end = split ? gi_begin + 1 : groups_per_set;
         int cached_cls = -1;    // class whose stage A sits in ac[]

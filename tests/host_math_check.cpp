@@ -94,3 +94,30 @@ extern "C" void hm_stage_b_mid(const double* p, int n, const double* ur, double 
     }
 }
 
+
+// live-prefix bound of prefix_bound.cuh (direct-sum kernel): J[t] for each maturity T[t] such that every grid point
+// j >= J[t] has an exponent below `cut`; one parameter set, one class (its own kts / v0s).
+#include <vector>
+
+#include "../pde_b200/csrc/prefix_bound.cuh"
+extern "C" int hm_prefix_J(const double* p, int nT, const double* T, int N, double eta, double alpha, double S0, double r,
+                           double q, double cut, int* J) {
+    hb::ClassConst c = {p[0], p[2] * p[2], p[3] * p[2]};
+    const hb::PrefixClass pc = hb::prefix_class(c, alpha);
+    std::vector<int> blk(hb::kMaxPrefixBlocks + 1);
+    const int nb = hb::prefix_blocks_host(N, blk.data());
+    std::vector<hb::PrefixBlock> blocks(nb);
+    for (int k = 0; k < nb; ++k) blocks[k] = hb::prefix_block(pc, eta * blk[k], eta * (blk[k + 1] - 1));
+    const double kts = p[0] * p[1] / c.sigma2, v0s = p[4] / c.sigma2, ui = -(alpha + 1.0);
+    for (int t = 0; t < nT; ++t) {
+        const double cst = -ui * (log(S0) + (r - q) * T[t]);
+        int last_live = -1;
+        for (int k = nb - 1; k >= 0; --k)
+            if (!(hb::prefix_ub(blocks[k], T[t], kts, v0s, cst) < cut - hb::kPrefixMargin)) {
+                last_live = k;
+                break;
+            }
+        J[t] = blk[last_live + 1];
+    }
+    return nb;
+}

@@ -37,6 +37,7 @@ constexpr int kDMaxMat = 512;     // maturities per surface (prefix table in sha
 constexpr int kDMaxCh = 96;       // chunks per wave
 constexpr int kDMaxSeg = 64;      // maturity pieces per wave
 constexpr int kDAFields = 5;      // stage-A cache: num, L0, d, g, q1
+constexpr int kDMapMax = 4096 / 32 + 1;  // coarse slot / item maps of a wave (CAP, ITEMS <= 4096)
 
 struct DirectDev {
     const double2* tw;    // [2 n_full]  (cos, sin)(pi k / n_full)
@@ -45,6 +46,8 @@ struct DirectDev {
     int nblk;
     int n_full;           // grid length N
     const int* mat_c2;    // [n_mat]     doubled centre of the maturity's bins (m_lo + m_hi)
+    const int* mat_rot;   // [n_mat]     row of `tabrot` holding tab_j W^{j m_c} for this maturity's centre, -1 = none
+    const double2* tabrot;  // [rows][n_full]
     const int* pair_off;  // [n_mat + 1]
     const int* pair_d2;   // doubled offsets |2m - c2| of the maturity's bins, distinct, ascending
     const int* opt_pq0;   // [n_sorted]  lower bracketing bin: (pair index << 1) | (bin above the centre), -1 = off grid
@@ -71,7 +74,12 @@ struct DirectWave {
     int next_m, next_c;  // cursor behind this wave: maturity and chunk within it
     int c_mat[kDMaxCh], c_j0[kDMaxCh], c_len[kDMaxCh], c_seg[kDMaxCh];
     int c_slot0[kDMaxCh + 1], c_item0[kDMaxCh + 1];
+    int c_rot[kDMaxCh];                     // tabrot row offset (row * n_full) or -1
+    double c_T[kDMaxCh], c_lsm[kDMaxCh];    // maturity, ln S0 + (r - q) T
     int s_mat[kDMaxSeg], s_c0[kDMaxSeg], s_c1[kDMaxSeg], s_flags[kDMaxSeg];  // flags: 1 = from j = 0, 2 = ends the maturity
+    int s_t0[kDMaxSeg + 1];  // finish tasks per slice before piece sg: options of an ending piece, pairs of a cut one
+    // coarse maps: the chunk holding slot 32 g / item 32 g (the exact chunk is at most a few steps further on)
+    unsigned char smap[kDMapMax], imap[kDMapMax];
 };
 
 // chunking of a prefix of J points: nc chunks of len points (the last one shorter); depends on J alone
@@ -84,7 +92,8 @@ __device__ __forceinline__ void direct_chunking(int J, int& nc, int& len) {
 __device__ __forceinline__ int direct_cls_variant(int ci) { return ci == 0 ? 0 : (ci == 1 ? 1 : (ci == 2 ? 3 : 4)); }
 
 template <int CAP, int ITEMS>
-__device__ void direct_build_wave(DirectWave& w, const int* s_J, const DirectDev& D, int m, int c, int m_end) {
+__device__ void direct_build_wave(DirectWave& w, const int* s_J, const SurfaceDev& S, const DirectDev& D, int m, int c,
+                                  int m_end) {
     int nch = 0, nslots = 0, nitems = 0, nseg = 0;
     while (m < m_end) {
         const int np = D.pair_off[m + 1] - D.pair_off[m];
@@ -113,6 +122,16 @@ __device__ void direct_build_wave(DirectWave& w, const int* s_J, const DirectDev
                 ++nseg;
             }
             w.c_mat[nch] = m;
+            if (added == 0) {
+                const double T = S.mat_T[m];
+                w.c_T[nch] = T;
+                w.c_lsm[nch] = S.ln_spot + (S.rate - S.dividend) * T;
+                w.c_rot[nch] = D.mat_rot[m] >= 0 ? D.mat_rot[m] * D.n_full : -1;
+            } else {
+                w.c_T[nch] = w.c_T[nch - 1];
+                w.c_lsm[nch] = w.c_lsm[nch - 1];
+                w.c_rot[nch] = w.c_rot[nch - 1];
+            }
             w.c_j0[nch] = c * len;
             w.c_len[nch] = l;
             w.c_seg[nch] = nseg - 1;
@@ -135,6 +154,20 @@ __device__ void direct_build_wave(DirectWave& w, const int* s_J, const DirectDev
     }
     w.c_slot0[nch] = nslots;
     w.c_item0[nch] = nitems;
+    w.s_t0[0] = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+        const int mm = w.s_mat[sg];
+        w.s_t0[sg + 1] = w.s_t0[sg] + ((w.s_flags[sg] & 2) ? S.mat_off[mm + 1] - S.mat_off[mm]
+                                                            : D.pair_off[mm + 1] - D.pair_off[mm]);
+    }
+    for (int g = 0, c2 = 0; 32 * g < nslots; ++g) {
+        while (w.c_slot0[c2 + 1] <= 32 * g) ++c2;
+        w.smap[g] = (unsigned char)c2;
+    }
+    for (int g = 0, c2 = 0; 32 * g < nitems; ++g) {
+        while (w.c_item0[c2 + 1] <= 32 * g) ++c2;
+        w.imap[g] = (unsigned char)c2;
+    }
     w.nch = nch;
     w.nslots = nslots;
     w.nitems = nitems;
@@ -144,15 +177,11 @@ __device__ void direct_build_wave(DirectWave& w, const int* s_J, const DirectDev
     w.more = (m < m_end) ? 1 : 0;
 }
 
-// index of the chunk whose [start[c], start[c+1]) holds x (start ascending, start[n] = total > x)
-__device__ __forceinline__ int direct_find(const int* start, int n, int x) {
-    int lo = 0, hi = n;  // invariant: start[lo] <= x < start[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (start[mid] <= x) lo = mid;
-        else hi = mid;
-    }
-    return lo;
+// index of the chunk whose [start[c], start[c+1]) holds x (start ascending, start[n] = total > x), from the coarse map
+__device__ __forceinline__ int direct_find(const int* start, const unsigned char* coarse, int x) {
+    int c = coarse[x >> 5];
+    while (start[c + 1] <= x) ++c;
+    return c;
 }
 
 // Prefix length of maturity m for class constants cc and the class's variants (kts[], v0s[] of nv variants):
@@ -195,6 +224,7 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
     __shared__ ClassConst s_cc[4];
     __shared__ double s_kts[6], s_v0s[6];
     __shared__ int s_jall;
+    __shared__ int s_task;  // K1 task queue of the running wave (blocks of 32 tasks, pulled per warp)
     __shared__ long long s_job;
     const int tid = threadIdx.x;
     const int n = S.n_opt, M = S.n_mat, NF = D.n_full;
@@ -227,6 +257,7 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
         if (tid == 0) {
             job_setup(js, params, ld, p, bd, V);
             s_jall = 0;
+            s_task = 0;
         }
         for (int m = tid; m < M; m += NT) s_J[m] = 0;
         __syncthreads();
@@ -315,7 +346,7 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                 afield(ci, 3)[j] = make_double2(a.g.re, a.g.im);
                 afield(ci, 4)[j] = make_double2(a.q1.re, a.q1.im);
             }
-            if (tid == 0) direct_build_wave<CAP, ITEMS>(waves[0], s_J, D, m_begin, 0, m_end);
+            if (tid == 0) direct_build_wave<CAP, ITEMS>(waves[0], s_J, S, D, m_begin, 0, m_end);
         }
         __syncthreads();
         for (int wi = 0;; ++wi) {
@@ -323,16 +354,34 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
             // the next wave's descriptor is built by one thread while K1 runs: no barrier separates the finish step of
             // wave wi - 1 from this point, hence three buffers (buffer (wi + 1) % 3 was last read in wave wi - 2)
             if (tid == NT - 1 && w.more)
-                direct_build_wave<CAP, ITEMS>(waves[(wi + 1) % 3], s_J, D, w.next_m, w.next_c, m_end);
+                direct_build_wave<CAP, ITEMS>(waves[(wi + 1) % 3], s_J, S, D, w.next_m, w.next_c, m_end);
             const int nslots = w.nslots, nch = w.nch, nitems = w.nitems;
             // ---- K1: one task = (class, point of a maturity): stage B, then stage F of the class's variants ----
-            for (int i = tid; i < NCLS * nslots; i += NT) {
-                const int ci = i / nslots, slot = i - ci * nslots;
-                const int c = direct_find(w.c_slot0, nch, slot);
+            // Tasks differ in cost (class 0 carries three final cexps, low grid points the full stage B): warps pull
+            // blocks of 32 tasks from a queue, class 0 first.
+            const int ntasks = NCLS * nslots;
+            for (int i = ntasks, first = 1, half = 0, blk0 = 0;; first = 0) {
+                if (ONEVAR) {  // uniform tasks: static assignment
+                    i = first ? tid : i + NT;
+                    if (i >= ntasks) break;
+                } else {  // blocks of 64 tasks: lane l takes tasks l and l + 32 of the block
+                    if (first || half) {
+                        if ((tid & 31) == 0) blk0 = atomicAdd(&s_task, 64);
+                        blk0 = __shfl_sync(0xffffffffu, blk0, 0);
+                        if (blk0 >= ntasks) break;
+                        half = 0;
+                        i = blk0 + (tid & 31);
+                    } else {
+                        half = 1;
+                        i = blk0 + 32 + (tid & 31);
+                    }
+                    if (i >= ntasks) continue;
+                }
+                const int ci = (i >= nslots) + (i >= 2 * nslots) + (i >= 3 * nslots), slot = i - ci * nslots;
+                const int c = direct_find(w.c_slot0, w.smap, slot);
                 const int m = w.c_mat[c], j = w.c_j0[c] + (slot - w.c_slot0[c]);
                 HB_ASSERT(c >= 0 && c < nch && j >= 0 && j < NF && slot < CAP);
-                const double T = S.mat_T[m];
-                const double lsm = S.ln_spot + (S.rate - S.dividend) * T;
+                const double T = w.c_T[c], lsm = w.c_lsm[c];
                 const double v = gc.eta * (double)j;
                 StageA a;
                 cplx l0;
@@ -347,7 +396,10 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                 }
                 // z_j = phi_j tab_j W^{j m_c}: weight and rotation to the centre of the maturity's bins
                 cplx tabrot;
-                {
+                if (w.c_rot[c] >= 0) {  // precomputed per distinct centre (hb_surface_set)
+                    const double2 tr = D.tabrot[w.c_rot[c] + j];
+                    tabrot = {tr.x, tr.y};
+                } else {
                     const double2 tb = D.tab[j];
                     const double2 rt = D.tw[((unsigned)j * (unsigned)D.mat_c2[m]) & tw_mask];
                     tabrot = cmul({tb.x, tb.y}, {rt.x, -rt.y});
@@ -363,7 +415,36 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                         ei[g] = fma(kts, b.B.im, fma(v0s, b.Dq.im, v * lsm));
                     }
                     double pr[3] = {0.0, 0.0, 0.0}, pi[3] = {0.0, 0.0, 0.0};
-                    if (!(er[0] < gc.cut && er[1] < gc.cut && er[2] < gc.cut)) cexp_w<3>(er, ei, pr, pi);
+                    if (!(er[0] < gc.cut && er[1] < gc.cut && er[2] < gc.cut)) {
+                        // theta' and v0' move the exponent by dl = dkts B + dv0s Dq, ~1e-8 |B|: where |dl| <= 2^-17
+                        // phi' = phi e^{dl} = phi (1 + dl + dl^2/2 + dl^3/6) to 1e-22 relative -- one cexp instead of
+                        // three, and dl is formed from the exact parameter differences, so phi' - phi (what the
+                        // finite difference reads) carries less rounding than two separate exponentials would
+                        cplx dl[3];
+                        bool small = true;
+#pragma unroll
+                        for (int g = 1; g < 3; ++g) {
+                            const double dk = s_kts[vs[g]] - s_kts[0], dv = s_v0s[vs[g]] - s_v0s[0];
+                            dl[g] = {fma(dk, b.B.re, dv * b.Dq.re), fma(dk, b.B.im, dv * b.Dq.im)};
+                            small = small && (fma(dl[g].re, dl[g].re, dl[g].im * dl[g].im) <= 5.8e-11);
+                        }
+                        if (small) {
+                            cexp_w<1>(er, ei, pr, pi);
+                            const cplx phi = {pr[0], pi[0]};
+#pragma unroll
+                            for (int g = 1; g < 3; ++g) {
+                                cplx t = {fma(dl[g].re, 1.0 / 3.0, 1.0), dl[g].im * (1.0 / 3.0)};   // 1 + dl/3
+                                t = cmul(dl[g], t);
+                                t = {fma(t.re, 0.5, 1.0), t.im * 0.5};                            // 1 + dl/2 (1 + dl/3)
+                                t = cmul(dl[g], t);                                              // e^{dl} - 1
+                                const cplx u = cmul(phi, t);
+                                pr[g] = phi.re + u.re;
+                                pi[g] = phi.im + u.im;
+                            }
+                        } else {
+                            cexp_w<3>(er, ei, pr, pi);
+                        }
+                    }
 #pragma unroll
                     for (int g = 0; g < 3; ++g) {
                         const bool zero = er[g] < gc.cut;  // exactly 0 as in stage_f
@@ -378,9 +459,11 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                 }
             }
             __syncthreads();
+            // every warp has left K1 and none re-enters it before the next barrier: reset the task queue here
+            if (tid == 0) s_task = 0;
             // ---- direct sums: item = (chunk, conjugate pair), all V slices ----
             for (int it = tid; it < nitems; it += NT) {
-                const int c = direct_find(w.c_item0, nch, it);
+                const int c = direct_find(w.c_item0, w.imap, it);
                 const int m = w.c_mat[c], pi_ = it - w.c_item0[c];
                 const unsigned d2 = (unsigned)D.pair_d2[D.pair_off[m] + pi_];
                 const int len = w.c_len[c];
@@ -419,48 +502,51 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                 for (int v = 0; v < V; ++v) part[(size_t)v * ITEMS + it] = make_double2(aP[v], aQ[v]);
             }
             __syncthreads();
-            // ---- chunk partials of a maturity piece added in chunk order into the piece's first chunk ----
-            for (int i = tid; i < V * nitems; i += NT) {
-                const int v = i / nitems, it = i - v * nitems;
-                const int c = direct_find(w.c_item0, nch, it);
-                const int sg = w.c_seg[c];
-                if (c != w.s_c0[sg]) continue;
-                const int pi_ = it - w.c_item0[c];
-                const int flags = w.s_flags[sg];
+            // ---- finish: chunk partials of a maturity added in chunk order (P and Q separately), X = P +- Q at the two
+            // bracketing bins, interpolation, clamp, parity.  A maturity cut by the wave leaves its running sums in
+            // `carry` (by wave parity: the first piece of a wave may read what its predecessor left while the last
+            // piece leaves its own).  No barrier up to the next K1: that one only writes ybuf. ----
+            {
                 const double2* carry_in = carry + (size_t)(wi & 1) * V * kDMaxPairs;
                 double2* carry_out = carry + (size_t)((wi + 1) & 1) * V * kDMaxPairs;
-                double2 acc = (flags & 1) ? make_double2(0.0, 0.0) : carry_in[v * kDMaxPairs + pi_];
-                for (int cc = c; cc < w.s_c1[sg]; ++cc) {
-                    const double2 q = part[(size_t)v * ITEMS + w.c_item0[cc] + pi_];
-                    acc.x += q.x;
-                    acc.y += q.y;
-                }
-                if (flags & 2) part[(size_t)v * ITEMS + it] = acc;
-                else carry_out[v * kDMaxPairs + pi_] = acc;
-            }
-            __syncthreads();
-            // ---- finished maturities: X = P +- Q at the two bracketing bins, interpolation, clamp, parity ----
-            for (int sg = 0; sg < w.nseg; ++sg) {
-                if (!(w.s_flags[sg] & 2)) continue;
-                const int m = w.s_mat[sg];
-                const int o0 = S.mat_off[m], no = S.mat_off[m + 1] - o0;
-                const int item0 = (w.s_c0[sg] < nch) ? w.c_item0[w.s_c0[sg]] : 0;
-                const double disc = S.mat_disc[m], fwd = S.mat_fwd[m];
-                for (int i = tid; i < V * no; i += NT) {
-                    const int v = i / no, o = o0 + (i - v * no);
+                auto pair_sum = [&](int sg, int v, int pi_) -> double2 {
+                    double2 acc = (w.s_flags[sg] & 1) ? make_double2(0.0, 0.0) : carry_in[v * kDMaxPairs + pi_];
+                    for (int cc = w.s_c0[sg]; cc < w.s_c1[sg]; ++cc) {
+                        const double2 q = part[(size_t)v * ITEMS + w.c_item0[cc] + pi_];
+                        acc.x += q.x;
+                        acc.y += q.y;
+                    }
+                    return acc;
+                };
+                // tasks of all pieces flattened: (slice v, option) of an ending piece, (slice v, pair) of a cut one
+                const int ntask = w.s_t0[w.nseg];
+                for (int i = tid; i < V * ntask; i += NT) {
+                    int v = 0, t = i;
+                    if (V > 1) {
+                        v = (i >= ntask) + (i >= 2 * ntask) + (i >= 3 * ntask) + (i >= 4 * ntask) + (i >= 5 * ntask);
+                        t = i - v * ntask;
+                    }
+                    int sg = 0;
+                    while (w.s_t0[sg + 1] <= t) ++sg;
+                    t -= w.s_t0[sg];
+                    const int m = w.s_mat[sg];
+                    if (!(w.s_flags[sg] & 2)) {  // only the last piece of a wave: keep the running sums
+                        carry_out[v * kDMaxPairs + t] = pair_sum(sg, v, t);
+                        continue;
+                    }
+                    const int o = S.mat_off[m] + t;
                     const int q0 = D.opt_pq0[o], q1 = D.opt_pq1[o];
                     double price = __longlong_as_double(0x7ff8000000000000LL);
                     if (q0 >= 0) {
-                        HB_ASSERT((q0 >> 1) < kDMaxPairs && (q1 >> 1) < kDMaxPairs && item0 + (q0 >> 1) < ITEMS);
-                        const double2 a0 = part[(size_t)v * ITEMS + item0 + (q0 >> 1)];
-                        const double2 a1 = part[(size_t)v * ITEMS + item0 + (q1 >> 1)];
+                        HB_ASSERT((q0 >> 1) < kDMaxPairs && (q1 >> 1) < kDMaxPairs);
+                        const double2 a0 = pair_sum(sg, v, q0 >> 1), a1 = pair_sum(sg, v, q1 >> 1);
                         const double x0 = (q0 & 1) ? a0.x + a0.y : a0.x - a0.y;
                         const double x1 = (q1 & 1) ? a1.x + a1.y : a1.x - a1.y;
                         const double c0 = S.opt_s0[o] * x0, c1 = S.opt_s1[o] * x1;
-                        const double call = disc * (c0 + (c1 - c0) * S.opt_frac[o]);
-                        price = finish_price(call, S.opt_call[o] != 0, fwd, S.opt_kdisc[o]);
+                        const double call = S.mat_disc[m] * (c0 + (c1 - c0) * S.opt_frac[o]);
+                        price = finish_price(call, S.opt_call[o] != 0, S.mat_fwd[m], S.opt_kdisc[o]);
                     }
-                    rows[(size_t)(ONEVAR ? 0 : v) * n + S.opt_orig[o]] = price;
+                    rows[(size_t)v * n + S.opt_orig[o]] = price;
                 }
             }
 #ifdef HB_DBG_SYNC

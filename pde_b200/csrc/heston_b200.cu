@@ -820,6 +820,37 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
                  o_ic = bb.add(std::vector<uint8_t>(is_call, is_call + n_opt));
     const size_t o_c2 = bb.add(mat_c2), o_po = bb.add(pair_off), o_pd = bb.add(pair_d2), o_q0 = bb.add(opt_pq0),
                  o_q1 = bb.add(opt_pq1);
+    // Carr-Madan weight times the rotation to the bin centre, tab_j W^{j m_c}, one row per distinct centre (most
+    // surfaces quote the same strikes at every maturity: one row); beyond 8 rows the kernel forms it per point
+    std::vector<int> mat_rot(M, -1);
+    std::vector<double> tabrot;
+    if (pl->mode == HB_MODE_FFT) {
+        std::vector<int> centres;
+        const long double pi_l = 3.14159265358979323846264338327950288L;
+        for (int m = 0; m < M; ++m) {
+            if (pair_off[m + 1] == pair_off[m]) continue;
+            int row = (int)(std::find(centres.begin(), centres.end(), mat_c2[m]) - centres.begin());
+            if (row == (int)centres.size()) {
+                if (centres.size() >= 8) continue;
+                centres.push_back(mat_c2[m]);
+                tabrot.resize((size_t)2 * N * centres.size());
+                for (int j = 0; j < N; ++j) {
+                    const double v = eta * (double)j, a = alpha * alpha + alpha - v * v, bb2 = (2.0 * alpha + 1.0) * v;
+                    const double wgt = (eta / 3.0) * (j == 0 ? 1.0 : ((j & 1) ? -4.0 : 2.0));
+                    const double r = wgt / (a * a + bb2 * bb2);
+                    const long long k = ((long long)j * mat_c2[m]) % (2LL * N);
+                    const long double ang = pi_l * (long double)k / (long double)N;
+                    const double c = (double)cosl(ang), sn = (double)sinl(ang);
+                    const double tr = a * r, ti = -bb2 * r;  // tab_j
+                    tabrot[((size_t)row * N + j) * 2] = tr * c + ti * sn;      // tab (c - i s)
+                    tabrot[((size_t)row * N + j) * 2 + 1] = ti * c - tr * sn;
+                }
+            }
+            mat_rot[m] = row;
+        }
+    }
+    const size_t o_mr = bb.add(mat_rot);
+    const size_t o_tr = bb.add(tabrot);
     pl->surf.want_pinned = true;
     // reserve() may free the old blob before a failing allocation: the plan holds no surface until the upload is done
     pl->has_surface = pl->has_market = false;
@@ -865,6 +896,8 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     S.mkt_orig = (const double*)(base + o_mkt);
     pl->D.mat_c2 = (const int*)(base + o_c2);
     pl->D.pair_off = (const int*)(base + o_po);
+    pl->D.mat_rot = (const int*)(base + o_mr);
+    pl->D.tabrot = (const double2*)(base + o_tr);
     pl->D.pair_d2 = (const int*)(base + o_pd);
     pl->D.opt_pq0 = (const int*)(base + o_q0);
     pl->D.opt_pq1 = (const int*)(base + o_q1);

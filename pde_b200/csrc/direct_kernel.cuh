@@ -30,14 +30,30 @@
 
 namespace hb {
 
-constexpr int kDNT = 512;         // threads per CTA
+// CTA shape, measured on B200 (profiles/r02_direct_shapes.txt): two CTAs of 256 threads per SM beat one of 512 / 640 /
+// 768 -- the phases of a wave (stage B/F tasks, direct sums, finish) are separated by CTA barriers, and a second
+// CTA fills the FP64 pipe while the first one waits (+4.5 % normal equations, +32 % objective).
+#ifndef HB_DNT
+#define HB_DNT 256
+#endif
+#ifndef HB_DCAP
+#define HB_DCAP 448
+#endif
+#ifndef HB_DITEMS
+#define HB_DITEMS 256
+#endif
+#ifndef HB_DCTAS
+#define HB_DCTAS 2
+#endif
+constexpr int kDNT = HB_DNT;      // threads per CTA
+constexpr int kDCtasPerSM = HB_DCTAS;
 constexpr int kDChunk = 64;       // points per chunk (one DFT item = chunk x pair)
 constexpr int kDMaxPairs = 64;    // conjugate pairs per maturity this kernel takes
 constexpr int kDMaxMat = 512;     // maturities per surface (prefix table in shared memory)
 constexpr int kDMaxCh = 96;       // chunks per wave
 constexpr int kDMaxSeg = 64;      // maturity pieces per wave
 constexpr int kDAFields = 5;      // stage-A cache: num, L0, d, g, q1
-constexpr int kDMapMax = 4096 / 32 + 1;  // coarse slot / item maps of a wave (CAP, ITEMS <= 4096)
+constexpr int kDMapMax = 8192 / 32 + 1;  // coarse slot / item maps of a wave (CAP, ITEMS <= 8192)
 
 struct DirectDev {
     const double2* tw;    // [2 n_full]  (cos, sin)(pi k / n_full)
@@ -62,8 +78,8 @@ template <bool ONEVAR>
 struct DirectCfg {
     static constexpr int V = ONEVAR ? 1 : 6;
     static constexpr int NCLS = ONEVAR ? 1 : 4;
-    static constexpr int CAP = ONEVAR ? 4096 : 960;     // wave capacity in points
-    static constexpr int ITEMS = ONEVAR ? 2304 : 512;   // (chunk, pair) items per wave
+    static constexpr int CAP = ONEVAR ? 4 * HB_DCAP : HB_DCAP;        // wave capacity in points
+    static constexpr int ITEMS = ONEVAR ? 4 * HB_DITEMS : HB_DITEMS;  // (chunk, pair) items per wave
     static constexpr size_t smem_bytes() {
         return (size_t)V * CAP * 16 + (size_t)V * ITEMS * 16 + (size_t)2 * V * kDMaxPairs * 16;
     }
@@ -190,9 +206,9 @@ __device__ __forceinline__ int direct_prefix(const PrefixBlock* blocks, const in
                                              const double* kts, const double* v0s, int nv, double cut, int sub) {
     int last_live = -1;
     for (int k = nblk - 1 - sub; k >= 0; k -= 4) {
-        const PrefixBlock b = blocks[k];
+        const PrefixTerms t = prefix_terms(blocks[k], T);  // shared by the variants of the class
         bool dead = true;
-        for (int i = 0; i < nv; ++i) dead = dead && (prefix_ub(b, T, kts[i], v0s[i], cst) < cut - kPrefixMargin);
+        for (int i = 0; i < nv; ++i) dead = dead && (prefix_ub_of(t, kts[i], v0s[i], cst) < cut - kPrefixMargin);
         if (!dead) {
             last_live = k;
             break;
@@ -204,7 +220,7 @@ __device__ __forceinline__ int direct_prefix(const PrefixBlock* blocks, const in
 }
 
 template <bool ONEVAR>
-__global__ void __launch_bounds__(kDNT, 1)
+__global__ void __launch_bounds__(kDNT, kDCtasPerSM)
 direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P,
                   int what, double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch,
                   int pieces, unsigned long long* job_counter) {
@@ -555,7 +571,7 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
             if (!w.more) break;
         }
         __syncthreads();  // the price rows of the job are complete
-        if (pieces == 1) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
+        if (pieces == 1) finalize_job<NT, kFinalizeT<NT>()>(what, rows, S, js, p, out, out2, red, tid);
     }
 }
 

@@ -216,7 +216,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
     // Transform kernel (fft_job_kernel).  job_ids / p_count (device): the sets a routed launch leaves to it.
     // split_mode: -1 = by batch size, 0 / 1 = as the routed launch decided; finalize: run the finalize kernel of a split launch
     auto launch_fft = [&](const int* job_ids, const int* p_count, unsigned long long* counter, size_t scratch_off,
-                          int split_mode, bool finalize) -> int {
+                          int split_mode, bool finalize, const int* jtab_arg = nullptr) -> int {
         const int gmax = gmax_for(pl->Nsub);
         const int g0 = ((V > 1 ? 3 * M : M) + gmax - 1) / gmax, g1 = (M + gmax - 1) / gmax;
         const int groups = g0 + (V > 1 ? 3 : 0) * g1;
@@ -236,7 +236,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
         const size_t smem = job_smem_bytes(pl->Nsub, gmax);
 #define HB_LAUNCH_JOB(NN, NTT, DEC, ONE)                                                                       \
     fft_job_kernel<NN, NTT, DEC, ONE><<<grid, NTT, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, \
-                                                               scratch, gmax, split ? 1 : 0, counter, job_ids, p_count)
+                                                               scratch, gmax, split ? 1 : 0, counter, job_ids, p_count, jtab_arg)
         const bool one = (V == 1);
         if (pl->Nsub == 4096) {
             if (pl->R == 1) {
@@ -257,7 +257,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             // same block size as the job kernel: the in-kernel finalize and this one then reduce in the
             // same order, so split and persistent launches agree bit for bit
             if (pl->Nsub == 4096)
-                finalize_rows_kernel<kNT4096><<<std::min(P, 4 * max_ctas), kNT4096, 0, st>>>(
+                finalize_rows_kernel<kNT4096, kFinalizeT<kNT4096>()><<<std::min(P, 4 * max_ctas), kNT4096, 0, st>>>(
                     S, pl->bd, d_params, ld, P, what, scratch, d_out, d_out2);
             else
                 finalize_rows_kernel<kNT512><<<std::min(P, 4 * max_ctas), kNT512, 0, st>>>(
@@ -270,7 +270,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
     if (pl->mode == HB_MODE_FFT && direct_enabled() && pl->direct_ok && gc.cut >= kDirectMinCut) {
         // Live prefix + direct sums (direct_kernel.cuh).  Small batches are cut into pieces of maturities so that
         // every SM has work; the arithmetic of a maturity does not depend on the piece or wave it is priced in.
-        const int max_ctas = pl->sm_count;
+        const int max_ctas = pl->sm_count * kDCtasPerSM;
         const bool one = (V == 1);
         const bool groups_ok = M > 0;
         int pieces = 1;
@@ -344,10 +344,10 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             // the long-prefix sets, on the transform kernel (its own job counter; its own scratch rows unless both
             // kernels write whole-batch rows for the common finalize)
             if ((rc = launch_fft(long_ids, counts + 1, ctr + 1, pieces > 1 ? 0 : (size_t)grid * row_bytes,
-                                 pieces > 1 ? 1 : 0, false)))
+                                 pieces > 1 ? 1 : 0, false, D.jtab)))
                 return rc;
             if (pieces > 1 && what != W_PRICE) {
-                finalize_rows_kernel<kDNT><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
+                finalize_rows_kernel<kDNT, kFinalizeT<kDNT>()><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
                                                                                        scratch, d_out, d_out2);
                 g_launches++;
                 HB_CUDA(cudaGetLastError());
@@ -357,7 +357,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
         g_launches++;
         HB_CUDA(cudaGetLastError());
         if (pieces > 1 && what != W_PRICE) {
-            finalize_rows_kernel<kDNT><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
+            finalize_rows_kernel<kDNT, kFinalizeT<kDNT>()><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
                                                                                    scratch, d_out, d_out2);
             g_launches++;
             HB_CUDA(cudaGetLastError());

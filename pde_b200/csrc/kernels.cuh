@@ -215,15 +215,17 @@ __device__ __forceinline__ void fill_group(Group& grp, const JobState& js, const
 
 // ---- block reductions ---------------------------------------------------------------------
 
-template <int NT, int W>
-__device__ __forceinline__ void block_sum(double (&acc)[W], double* red /* [NT/32][W] */, int tid) {
+// FT <= NT: only the first FT threads carry partial sums (finalize_job: the reduction order then depends on FT alone,
+// so kernels with different block sizes agree bit for bit); every thread of the block takes part in the barriers.
+template <int NT, int W, int FT = NT>
+__device__ __forceinline__ void block_sum(double (&acc)[W], double* red /* [FT/32][W] */, int tid) {
 #pragma unroll
     for (int i = 0; i < W; ++i) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
     }
     const int warp = tid >> 5, lane = tid & 31;
-    if (lane == 0) {
+    if (lane == 0 && warp < FT / 32) {
 #pragma unroll
         for (int i = 0; i < W; ++i) red[warp * W + i] = acc[i];
     }
@@ -231,7 +233,7 @@ __device__ __forceinline__ void block_sum(double (&acc)[W], double* red /* [NT/3
     if (warp == 0) {
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            double v = (lane < NT / 32) ? red[lane * W + i] : 0.0;
+            double v = (lane < FT / 32) ? red[lane * W + i] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             acc[i] = v;
@@ -240,6 +242,12 @@ __device__ __forceinline__ void block_sum(double (&acc)[W], double* red /* [NT/3
     __syncthreads();
 }
 
+// Threads that carry the sums of finalize_job in the Carr-Madan job kernels: 256 whatever the block size (the
+// transform kernel runs 512 threads, the direct-sum kernel may run another shape, and a routed launch prices some
+// sets of a batch with one and some with the other -- same reduction order, same bits).
+template <int NT>
+__host__ __device__ constexpr int kFinalizeT() { return NT >= 256 ? 256 : NT; }
+
 // _compute_residuals, heston_calibrator.py:533-535 (np.maximum propagates NaN)
 __device__ __forceinline__ double residual_of(double price, double mkt) {
     const double p = (price != price) ? price : fmax(price, 1e-10);
@@ -247,14 +255,15 @@ __device__ __forceinline__ double residual_of(double price, double mkt) {
 }
 
 // Turn the price rows of one job into the requested output.  rows[v * n_opt + i].
-template <int NT>
+template <int NT, int FT = NT>
 __device__ __forceinline__ void finalize_job(int what, const double* rows, const SurfaceDev& S, const JobState& js,
                                              int p, double* out, double* out2, double* red, int tid) {
+    static_assert(FT <= NT && FT % 32 == 0, "FT threads of the block carry the sums");
     const int n = S.n_opt;
     if (what == W_PRICE) return;
     if (what == W_LOSS) {
         double acc[2] = {0.0, 0.0};
-        for (int i = tid; i < n; i += NT) {
+        for (int i = tid; i < n && tid < FT; i += FT) {
             const double pr = rows[i], m = S.mkt_orig[i];
             if (pr != pr || pr <= 0.0) {
                 acc[1] += 1.0;  // heston_calibrator.py:507-508
@@ -263,7 +272,7 @@ __device__ __forceinline__ void finalize_job(int what, const double* rows, const
                 acc[0] += e * e;
             }
         }
-        block_sum<NT, 2>(acc, red, tid);
+        block_sum<NT, 2, FT>(acc, red, tid);
         if (tid == 0) out[p] = (acc[1] > 0.0) ? 1e10 : acc[0];
         return;
     }
@@ -284,7 +293,7 @@ __device__ __forceinline__ void finalize_job(int what, const double* rows, const
     double acc[23];
 #pragma unroll
     for (int i = 0; i < 23; ++i) acc[i] = 0.0;
-    for (int i = tid; i < n; i += NT) {
+    for (int i = tid; i < n && tid < FT; i += FT) {
         const double pr = rows[i], m = S.mkt_orig[i];
         if (pr != pr || pr <= 0.0) {
             acc[22] += 1.0;
@@ -305,7 +314,7 @@ __device__ __forceinline__ void finalize_job(int what, const double* rows, const
             for (int c = a; c < 5; ++c) acc[t++] += J[a] * J[c];
         }
     }
-    block_sum<NT, 23>(acc, red, tid);
+    block_sum<NT, 23, FT>(acc, red, tid);
     if (tid == 0) {
         double* o = out + (size_t)p * 22;
         o[0] = (acc[22] > 0.0) ? 1e10 : acc[0];
@@ -361,9 +370,10 @@ __global__ void __launch_bounds__(NT, 1)
 fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
                double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch, int gmax,
                int split, unsigned long long* job_counter, const int* __restrict__ job_ids = nullptr,
-               const int* __restrict__ p_count = nullptr) {
+               const int* __restrict__ p_count = nullptr, const int* __restrict__ jtab = nullptr) {
     // job_ids / p_count: the parameter sets routed to this kernel by prefix_scan_kernel (direct_kernel.cuh) and
-    // their number, both on the device; null = all P sets in order
+    // their number, both on the device; null = all P sets in order.  jtab[p][maturity]: live-prefix bound of that
+    // launch (prefix_bound.cuh): grid points at or beyond it are exact zeros and are not evaluated.
     if (p_count) P = *p_count;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* slices = reinterpret_cast<double2*>(smem_raw);
@@ -601,6 +611,13 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         skip &= (unsigned)(deadm[mat >> 3] >> ((mat & 7) * 8));
                     }
                     skip &= 0xffu;
+                }
+                if (jtab) {  // beyond the live prefix of every slice of the group
+                    int jlim = 0;
+                    for (int g = 0; g < count; ++g) jlim = max(jlim, jtab[(size_t)p * M + grp.s[g].mat]);
+#pragma unroll
+                    for (int k = 0; k < PTS; ++k)
+                        if (ph + R * (tid + k * NT) >= jlim) skip |= 1u << k;
                 }
                 // class 0 records the base slice's decayed points (slice 0 of a class-0 group is the base set)
                 const bool record = track_tail && cls == 0 && grp.s[0].variant == 0;
@@ -969,14 +986,14 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
         }
         HB_PROBE_T(pf0);
         __syncthreads();  // the price rows of the last group are complete
-        if (!split) finalize_job<NT>(what, rows, S, js, p, out, out2, red, tid);
+        if (!split) finalize_job<NT, kFinalizeT<NT>()>(what, rows, S, js, p, out, out2, red, tid);
         HB_PROBE_T(pf1);
         HB_PROBE_ADD(7, pf0, pf1);  // finalize
     }
 }
 
 // Finalize for split launches: one CTA per parameter set, rows[p][6][n_opt] in global memory.
-template <int NT>
+template <int NT, int FT = NT>
 __global__ void __launch_bounds__(NT)
 finalize_rows_kernel(SurfaceDev S, Bounds bd, const double* __restrict__ params, int ld, int P, int what,
                      const double* __restrict__ rows_buf, double* __restrict__ out, double* __restrict__ out2) {
@@ -992,7 +1009,7 @@ finalize_rows_kernel(SurfaceDev S, Bounds bd, const double* __restrict__ params,
             invalid_job<NT>(what, S, p, out, out2, tid);
             continue;
         }
-        finalize_job<NT>(what, rows_buf + (size_t)p * 6 * S.n_opt, S, js, p, out, out2, red, tid);
+        finalize_job<NT, FT>(what, rows_buf + (size_t)p * 6 * S.n_opt, S, js, p, out, out2, red, tid);
     }
 }
 

@@ -117,25 +117,39 @@ HB_HD PrefixBlock prefix_block(const PrefixClass& p, double va, double vb) {
     return b;
 }
 
-// Upper bound of er = log|phi| over the block for a slice (T, kts, v0s; cst = -ui lsm), +inf where a premise fails
-// (NaN inputs compare false and end in +inf or NaN: never "dead").
-HB_HD double prefix_ub(const PrefixBlock& b, double T, double kts, double v0s, double cst) {
+// Upper bounds of Re B and Re Dq over the block at maturity T (+inf where a premise fails; NaN inputs compare false
+// and end in +inf or NaN: never "dead").  They do not depend on theta or v0: the variants of a class share them.
+struct PrefixTerms {
+    double reB, reDq;
+};
+HB_HD PrefixTerms prefix_terms(const PrefixBlock& b, double T) {
     const double inf = HUGE_VAL;
-    const double Ea = exp(-b.dra * T), Eb = exp(-b.drb * T);
+    const double Ea = exp_nb(-b.dra * T), Eb = exp_nb(-b.drb * T);
     const double ome = (1.0 - Eb) + Ea * fmin(2.0, b.di_up * T);
     const double x = b.q1_up * ome;
-    const double L1 = (x < 0.5) ? -2.0 * log1p(-x) : inf;
     const double gE = b.gg * Ea;
     const bool gok = gE < 0.5;
-    const double L2 = gok ? b.l1g - 2.0 * log1p(-gE) : inf;
-    const double Lt = fmin(L1, L2);
-    const double Dq = gok ? b.nre + b.n1g * Ea / (1.0 - gE) : inf;
-    double reB = b.nre * T + Lt, reDq = Dq;
+    // (5): the smaller of the two forms; one log1p serves both (its argument picked first)
+    const double L2a = gok ? b.l1g : inf;             // + (-2 log1p(-gE))
+    double Lt;
+    if (x < 0.5 && gok) {
+        const double l1 = -2.0 * log1p_nb(-x), l2 = L2a - 2.0 * log1p_nb(-gE);
+        Lt = fmin(l1, l2);
+    } else if (x < 0.5) {
+        Lt = -2.0 * log1p_nb(-x);
+    } else if (gok) {
+        Lt = L2a - 2.0 * log1p_nb(-gE);
+    } else {
+        Lt = inf;
+    }
+    PrefixTerms t;
+    t.reB = b.nre * T + Lt;
+    t.reDq = gok ? b.nre + b.n1g * Ea / (1.0 - gE) : inf;
     // (7) small |d T| (short maturities, small sigma: e is not small and the forms above lose the cancellation between
     // Re(num) and the rest).  With z = d T/2 (z^2 = d^2 T^2/4 is known without a square root):
     //   Re B = kp T - 2 log|sinh z / z| - 2 log|xi T/2 + z coth z|,      Dq = -sigma^2 w (T/2)/(xi T/2 + z coth z),
     //   sinh z/z = 1 + z^2/6 + r1,  z coth z = 1 + z^2/3 + r2,  |r1| <= (|z|^4/120)/(1 - |z|^2/42),  |r2| <= (|z|^4/45)/(1 - |z|^2/pi^2),
-    // and |1 + x| >= 1 + Re x, Re z^2 = P T^2/4 non-decreasing in v.
+    // with Re z^2 = P T^2/4 non-decreasing in v and |1 + x|^2 >= (1 + Re x)^2 + (|Im x| - |r|)^2.
     const double z2 = 0.25 * b.D2b * T * T;  // >= |z|^2 on the block
     if (z2 <= 2.0) {
         const double r1 = z2 * z2 / (120.0 * (1.0 - z2 / 42.0));
@@ -147,18 +161,27 @@ HB_HD double prefix_ub(const PrefixBlock& b, double T, double kts, double v0s, d
             const double i1 = fmax(0.0, fabs(b.ca) * T * T / 24.0 - r1);
             const double cima = 0.5 * b.rsa * T + b.ca * T * T / 12.0;  // cim va (signed)
             const double i2 = fmax(0.0, fabs(cima) - r2);
-            reB = fmin(reB, b.kp * T - log(s1 * s1 + i1 * i1) - log(s2 * s2 + i2 * i2));
+            // log(m1) + log(m2) = log1p(m1 m2 - 1): the moduli are O(1) here (z2 <= 2)
+            const double m1 = s1 * s1 + i1 * i1, m2 = s2 * s2 + i2 * i2;
+            t.reB = fmin(t.reB, b.kp * T - log1p_nb(m1 * m2 - 1.0));
             const double s2hi = 1.0 + 0.5 * b.kp * T + b.Pb * T * T / 12.0 + r2;
             const double bup = 0.5 * b.bx * T + b.cv * T * T / 12.0 + r2;
             // Re(w conj(den)) = Re w Re den + Im w Im den, Im w = -(2 alpha + 1) v, Im den = -cim v + Im r2:
             // the second product is >= swia (cim va - r2) when cim > 0, >= -swi bup always
             const double cross = (cima > r2) ? b.swia * (cima - r2) : -b.swi * bup;
             const double numer = b.swr * s2 + cross;
-            if (b.swr > 0.0 && numer > 0.0) reDq = fmin(reDq, -0.5 * T * numer / (s2hi * s2hi + bup * bup));
+            if (b.swr > 0.0 && numer > 0.0) t.reDq = fmin(t.reDq, -0.5 * T * numer / (s2hi * s2hi + bup * bup));
         }
     }
-    const double ub = cst + kts * reB + v0s * reDq;
-    return ((kts >= 0.0) && (v0s >= 0.0) && (ub == ub)) ? ub : inf;
+    return t;
+}
+// Upper bound of er = log|phi| over the block for a slice (kts, v0s; cst = -ui lsm)
+HB_HD double prefix_ub_of(const PrefixTerms& t, double kts, double v0s, double cst) {
+    const double ub = cst + kts * t.reB + v0s * t.reDq;
+    return ((kts >= 0.0) && (v0s >= 0.0) && (ub == ub)) ? ub : HUGE_VAL;
+}
+HB_HD double prefix_ub(const PrefixBlock& b, double T, double kts, double v0s, double cst) {
+    return prefix_ub_of(prefix_terms(b, T), kts, v0s, cst);
 }
 
 // Slack between the bound and the cut: covers the rounding of the bound itself and of the exponent the kernels

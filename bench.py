@@ -221,8 +221,9 @@ def workload_config(P):
             "sets_per_gpu": P, "maturities": N_MAT, "strikes": N_STRIKE, "n_grid": N_GRID,
             "slice_evals_per_step_per_gpu": P * N_MAT * 6, "mode": "fft",
             "population": "scrambled Sobol (seed 42) over HestonCalibrator.DEFAULT_BOUNDS: the rate is INPUT-DEPENDENT "
-                          "-- the integrand of most sets decays within the first ~10 % of the grid and decayed points "
-                          "are not evaluated (exact underflow, plan's significance cut, asymptotic stage B); "
+                          "-- the integrand of most sets decays within the first ~10 % of the grid (plan's significance "
+                          "cut); a rigorous bound of that live prefix routes a set to the direct-sum kernel (cost ~ prefix) "
+                          "or, above a mean prefix of 1200 points, to the transform kernel (cost ~ N log N); "
                           "value_noskip gives the same step where nothing can be or is elided",
             "l2": "L2 flushed (256 MiB write) between timed steps; per-step CUDA events on the launch stream"}
 
@@ -335,11 +336,14 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = launch_count()
+    pricer.profile(True)  # CUDA-event pairs around each kernel of the step, on the launch stream
     t_wall = time.perf_counter()
     ms = timed_steps(torch, dev, step, args.steps, flush)
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = launch_count() - l0
+    prof = pricer.profile_read()
+    pricer.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     slices_step = world * P * N_MAT * 6
@@ -436,12 +440,19 @@ def run_ours(args):
 
     if rank == 0:
         per_launch_s = ms / args.steps * 1e-3
-        achieved = (P * N_MAT * 6 * FLOPS_PER_SLICE) / per_launch_s / 1e12  # per GPU, TFLOP/s, W1 convention
+        # The step is three kernels: prefix scan (routing + live-prefix table), the direct-sum job kernel (the
+        # dominant one: the sets whose integrand has decayed) and the transform job kernel (long-prefix sets).
+        # Roofline of the dominant kernel: W1 flops of the sets it priced / its own duration (CUDA events around
+        # the kernel on the launch stream, averaged over the timed steps).
+        k_ms = {k: prof[k] / args.steps for k in ("scan_ms", "direct_ms", "transform_ms")}
+        n_direct = prof["sets_direct"] if prof["sets_direct"] >= 0 else P
+        dom_s = (k_ms["direct_ms"] if k_ms["direct_ms"] > 0 else ms / args.steps) * 1e-3
+        achieved = (n_direct * N_MAT * 6 * FLOPS_PER_SLICE) / dom_s / 1e12  # per GPU, TFLOP/s, W1 convention
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
         hbm_achieved = (P * N_MAT * 6 * BYTES_PER_SLICE) / per_launch_s / 1e9
         cap = _ncu_capture(P)
-        executed = cap["executed_flop_per_launch"] / per_launch_s / 1e12 if cap else None
+        executed = cap["executed_flop_per_launch"] / dom_s / 1e12 if cap else None
         line = {
             "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -455,7 +466,12 @@ def run_ours(args):
             "wall_s_timed_region": t_wall,
             "significance_cut": {"log_cut": pricer.log_cut, "abs_price_error_budget": 2.0 ** -80},
             "value_noskip": noskip,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "kernels_ms_per_step": dict(k_ms, step_ms=ms / args.steps,
+                                        sets_direct=prof["sets_direct"], sets_transform=prof["sets_transform"],
+                                        note="CUDA events around each kernel; their sum is the step (profiles/ ncu "
+                                             "launch list: same shares)"),
+            "roofline": {"bound": "fp64", "kernel": "direct_job_kernel<false> (live prefix + direct sums)",
+                         "kernel_ms": dom_s * 1e3, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak,
                          "frac_is": "W1 algorithmic flops (SURVEY.md 8d) / measured DFMA peak: exceeds 1 because shared "
                                     "and elided work is not executed; frac_executed and fp64_pipe_active_ncu are the "

@@ -201,6 +201,14 @@ int hb_model_price_options(const double* params5, int n, const double* strikes, 
 int hb_measure_fp64_peak(int device, double seconds, double* tflops);
 /* Kernel launches issued by this library in this process so far. */
 uint64_t hb_launch_count(void);
+/* Kernel durations of a plan's pricing launches, measured with CUDA events on the launch stream (bench.py's roofline:
+ * the duration of the dominant kernel inside the timed region).  enable != 0: every hb_price / hb_objective /
+ * hb_normal_eq / hb_jacobian launch records an event pair around each of its kernels (at most 1024 pairs are kept). */
+int hb_plan_profile(hb_plan* plan, int enable);
+/* Waits for the recorded launches, then ms3 = summed durations of { prefix scan, direct-sum job kernel, transform /
+ * refgrid job kernel (with its finalize) } and n3 = { kernel invocations recorded, parameter sets the LAST launch
+ * routed to the direct-sum kernel, ... to the transform kernel } (-1: that launch was not routed); clears the record. */
+int hb_plan_profile_read(hb_plan* plan, double* ms3, long long* n3);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,8 @@ SIGNATURES = {
     "hb_sabr_vols_host": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp, C.c_int, _dp]),
     "hb_measure_fp64_peak": (C.c_int, [C.c_int, C.c_double, _dp]),
     "hb_launch_count": (C.c_uint64, []),
+    "hb_plan_profile": (C.c_int, [_vp, C.c_int]),
+    "hb_plan_profile_read": (C.c_int, [_vp, _dp, C.POINTER(C.c_longlong)]),
 }
 
 _lib = None

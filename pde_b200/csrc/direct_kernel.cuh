@@ -45,6 +45,9 @@ namespace hb {
 #ifndef HB_DCTAS
 #define HB_DCTAS 2
 #endif
+#ifndef HB_DPREFETCH
+#define HB_DPREFETCH 0
+#endif
 constexpr int kDNT = HB_DNT;      // threads per CTA
 constexpr int kDCtasPerSM = HB_DCTAS;
 constexpr int kDChunk = 64;       // points per chunk (one DFT item = chunk x pair)
@@ -387,6 +390,20 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                         if (blk0 >= ntasks) break;
                         half = 0;
                         i = blk0 + (tid & 31);
+#if HB_DPREFETCH
+                        // the lane's second task of the block: pull its stage-A cache lines (L2 hits of several hundred
+                        // cycles) towards L1 while the first task is evaluated
+                        if (i + 32 < ntasks) {
+                            const int i2 = i + 32;
+                            const int ci2 = (i2 >= nslots) + (i2 >= 2 * nslots) + (i2 >= 3 * nslots), slot2 = i2 - ci2 * nslots;
+                            const int c2 = direct_find(w.c_slot0, w.smap, slot2);
+                            const int j2 = w.c_j0[c2] + (slot2 - w.c_slot0[c2]);
+#pragma unroll
+                            for (int f = 0; f < kDAFields; ++f)
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(afield(ci2, f) + j2));
+                            if (w.c_rot[c2] >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(D.tabrot + w.c_rot[c2] + j2));
+                        }
+#endif
                     } else {
                         half = 1;
                         i = blk0 + 32 + (tid & 31);

@@ -111,6 +111,14 @@ struct hb_plan {
     Arena dtab, acache, route;
     DirectDev D{};
     bool direct_ok = false;  // surface fits the direct kernel's limits (pairs per maturity, maturities)
+    // hb_plan_profile: event pairs around the kernels of each launch (kind 0 scan, 1 direct, 2 transform / refgrid)
+    struct ProfRec {
+        int kind;
+        cudaEvent_t a, b;
+    };
+    bool profiling = false;
+    bool last_routed = false;
+    std::vector<ProfRec> prof;
     const double* d_strike = nullptr;    // caller-order copies for the implied-vol epilogue
     const double* d_maturity = nullptr;
     const uint8_t* d_is_call = nullptr;
@@ -163,7 +171,7 @@ bool direct_enabled() {
 // measured crossover of the two kernels on B200.  HB_DIRECT_THR=0 switches the routing off.
 int direct_threshold() {
     const char* e = std::getenv("HB_DIRECT_THR");
-    return e ? std::atoi(e) : 1000;
+    return e ? std::atoi(e) : 1200;
 }
 
 int gmax_for(int N) { return (N == 4096 || N == 512) ? 3 : 1; }
@@ -212,6 +220,19 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
         HB_CUDA(cudaMemsetAsync(pl->ctr.dev, 0, 2 * sizeof(unsigned long long), st));
     }
     unsigned long long* ctr = (unsigned long long*)pl->ctr.dev;
+    // hb_plan_profile: an event pair around each kernel of this launch
+    auto prof_begin = [&](int kind) -> int {
+        if (!pl->profiling || pl->prof.size() >= 1024) return -1;
+        hb_plan::ProfRec r{kind, nullptr, nullptr};
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+        cudaEventRecord(r.a, st);
+        pl->prof.push_back(r);
+        return (int)pl->prof.size() - 1;
+    };
+    auto prof_end = [&](int idx) {
+        if (idx >= 0) cudaEventRecord(pl->prof[idx].b, st);
+    };
+    pl->last_routed = false;
 
     // Transform kernel (fft_job_kernel).  job_ids / p_count (device): the sets a routed launch leaves to it.
     // split_mode: -1 = by batch size, 0 / 1 = as the routed launch decided; finalize: run the finalize kernel of a split launch
@@ -234,6 +255,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             scratch = (double*)((unsigned char*)pl->scratch.dev + scratch_off);
         }
         const size_t smem = job_smem_bytes(pl->Nsub, gmax);
+        const int pi_fft = prof_begin(2);
 #define HB_LAUNCH_JOB(NN, NTT, DEC, ONE)                                                                       \
     fft_job_kernel<NN, NTT, DEC, ONE><<<grid, NTT, smem, st>>>(S, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, \
                                                                scratch, gmax, split ? 1 : 0, counter, job_ids, p_count, jtab_arg)
@@ -265,6 +287,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             g_launches++;
             HB_CUDA(cudaGetLastError());
         }
+        prof_end(pi_fft);
         return HB_OK;
     };
     if (pl->mode == HB_MODE_FFT && direct_enabled() && pl->direct_ok && gc.cut >= kDirectMinCut) {
@@ -314,6 +337,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             HB_CUDA(cudaMemsetAsync(counts, 0, 256, st));
             const size_t ssm = (size_t)kScanWarps * D.nblk * sizeof(PrefixBlock);
             const int sgrid = std::min((P + kScanWarps - 1) / kScanWarps, 8 * max_ctas);
+            const int pi_scan = prof_begin(0);
             if (one) {
                 if ((rc = set_smem(prefix_scan_kernel<true>, ssm))) return rc;
                 prefix_scan_kernel<true><<<sgrid, 32 * kScanWarps, ssm, st>>>(S, D, gc, pl->bd, d_params, ld, P, jtab,
@@ -323,12 +347,15 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
                 prefix_scan_kernel<false><<<sgrid, 32 * kScanWarps, ssm, st>>>(S, D, gc, pl->bd, d_params, ld, P, jtab,
                                                                                direct_threshold(), short_ids, long_ids, counts);
             }
+            prof_end(pi_scan);
             g_launches++;
             HB_CUDA(cudaGetLastError());
+            pl->last_routed = true;
             D.job_ids = short_ids;
             D.jtab = jtab;
             D.p_count = counts;
         }
+        const int pi_direct = prof_begin(1);
         if (one) {
             if ((rc = set_smem(direct_job_kernel<true>, DirectCfg<true>::smem_bytes()))) return rc;
             direct_job_kernel<true><<<grid, kDNT, DirectCfg<true>::smem_bytes(), st>>>(
@@ -338,6 +365,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             direct_job_kernel<false><<<grid, kDNT, DirectCfg<false>::smem_bytes(), st>>>(
                 S, D, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, pieces, ctr);
         }
+        prof_end(pi_direct);
         if (routed) {
             g_launches++;
             HB_CUDA(cudaGetLastError());
@@ -478,6 +506,38 @@ int hb_version(void) { return 100; }
 const char* hb_last_error(void) { return g_err.c_str(); }
 uint64_t hb_launch_count(void) { return g_launches.load(); }
 
+int hb_plan_profile(hb_plan* pl, int enable) {
+    if (!pl) return fail(HB_ERR_INVALID_ARGUMENT, "plan is NULL");
+    pl->profiling = enable != 0;
+    return HB_OK;
+}
+
+int hb_plan_profile_read(hb_plan* pl, double* ms3, long long* n3) {
+    if (!pl || !ms3 || !n3) return fail(HB_ERR_INVALID_ARGUMENT, "NULL argument");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(HB_ERR_CUDA, "cannot select CUDA device");
+    if (pl->last_launch) HB_CUDA(cudaEventSynchronize(pl->last_launch));
+    ms3[0] = ms3[1] = ms3[2] = 0.0;
+    n3[0] = (long long)pl->prof.size();
+    n3[1] = n3[2] = -1;
+    for (auto& r : pl->prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.kind >= 0 &&
+            r.kind < 3)
+            ms3[r.kind] += (double)ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    pl->prof.clear();
+    if (pl->last_routed && pl->route.dev) {
+        int c[2] = {0, 0};
+        HB_CUDA(cudaMemcpy(c, pl->route.dev, sizeof c, cudaMemcpyDeviceToHost));
+        n3[1] = c[0];
+        n3[2] = c[1];
+    }
+    return HB_OK;
+}
+
 int hb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -598,6 +658,10 @@ int hb_plan_destroy(hb_plan* pl) {
     if (pl->last_launch) {
         cudaEventSynchronize(pl->last_launch);
         cudaEventDestroy(pl->last_launch);
+    }
+    for (auto& r : pl->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
     }
     pl->gk.release();
     pl->surf.release();

@@ -106,6 +106,20 @@ class BatchPricer:
         """log|phi| below which a grid point counts as 0 for the surface in force (-746 = exp underflow)."""
         return float(self._L.hb_plan_log_cut(self._h))
 
+    def profile(self, enable: bool = True) -> "BatchPricer":
+        """Record CUDA-event pairs around the kernels of every pricing launch (``hb_plan_profile``)."""
+        check(self._L.hb_plan_profile(self._h, 1 if enable else 0))
+        return self
+
+    def profile_read(self) -> dict:
+        """Summed kernel durations since the last read (``hb_plan_profile_read``): prefix scan, direct-sum job kernel,
+        transform / refgrid job kernel; how the last launch was routed.  Waits for the launches."""
+        ms = (C.c_double * 3)()
+        n = (C.c_longlong * 3)()
+        check(self._L.hb_plan_profile_read(self._h, ms, n))
+        return {"scan_ms": ms[0], "direct_ms": ms[1], "transform_ms": ms[2], "kernel_invocations": int(n[0]),
+                "sets_direct": int(n[1]), "sets_transform": int(n[2])}
+
     def set_bounds(self, lb, ub) -> "BatchPricer":
         lb, ub = _np_d(lb), _np_d(ub)
         if lb.size != 5 or ub.size != 5:

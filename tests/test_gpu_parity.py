@@ -405,13 +405,24 @@ def c3_benched_path_sets():
     return np.vstack([sobol_sets(512), corners, slow])
 
 
-def test_benched_path_normal_equations_match_oracle_on_c3_surface(torch_cuda, oracle):
+_C3_WANT = {}
+
+
+@pytest.mark.parametrize("route", ["routed", "all_direct", "all_transform"])
+def test_benched_path_normal_equations_match_oracle_on_c3_surface(torch_cuda, oracle, monkeypatch, route):
     """BASELINE.json config 3's own shape (32 maturities x 50 strikes, N = 4096, default bounds) on the launch
-    path bench.py times -- fft_job_kernel<4096,512,false,false>, one persistent CTA per set -- against
-    oracle.normal_eq_batch: all 22 columns, and hb_jacobian's residuals / Jacobian on the same sets."""
+    path bench.py times against oracle.normal_eq_batch: all 22 columns, and hb_jacobian's residuals / Jacobian on
+    the same sets.  `routed` is the product default (prefix scan, short-prefix sets on direct_job_kernel, the
+    slow-decay cluster and the long corners on fft_job_kernel); `all_direct` forces every set -- including the
+    ones whose live prefix is the whole grid, i.e. maturities cut over many waves -- through the direct-sum kernel,
+    `all_transform` through the transform kernel (persistent path, tail skip / asymptotic and series stage B live)."""
     from pde_b200 import BatchPricer
 
     torch = torch_cuda
+    if route == "all_direct":
+        monkeypatch.setenv("HB_DIRECT_THR", "0")
+    elif route == "all_transform":
+        monkeypatch.setenv("HB_DIRECT", "0")
     oracle.use_all_cores()
     xs = c3_benched_path_sets()
     assert len(xs) >= 2 * torch.cuda.get_device_properties(0).multi_processor_count  # persistent path
@@ -424,7 +435,20 @@ def test_benched_path_normal_equations_match_oracle_on_c3_surface(torch_cuda, or
     res, jac = pr.jacobian(X)
     res, jac = res.cpu().numpy(), jac.cpu().numpy()
     prices = pr.price(X).cpu().numpy()
-    want = oracle.normal_eq_batch(MODE_FFT, xs, LB, UB, Kf, Tf, True, mk, S0, R, Q)
+    if route != "all_transform":  # the launch was routed as intended
+        pr.profile(True)
+        pr.normal_equations(X)
+        rt = pr.profile_read()
+        pr.profile(False)
+        assert rt["direct_ms"] > 0.0
+        if route == "routed":
+            assert rt["sets_direct"] + rt["sets_transform"] == len(xs)
+            assert 64 <= rt["sets_transform"] < 200 and rt["transform_ms"] > 0.0 and rt["scan_ms"] > 0.0  # slow cluster + corners
+        else:  # no scan, no second kernel
+            assert rt["sets_direct"] == -1 and rt["transform_ms"] == 0.0 and rt["scan_ms"] == 0.0
+    if "want" not in _C3_WANT:
+        _C3_WANT["want"] = oracle.normal_eq_batch(MODE_FFT, xs, LB, UB, Kf, Tf, True, mk, S0, R, Q)
+    want = _C3_WANT["want"]
 
     fin = np.isfinite(want).all(axis=1) & (want[:, 0] != 1e10)
     assert fin.sum() >= 400  # most of the population is an ordinary candidate

@@ -30,17 +30,18 @@
 
 namespace hb {
 
-// CTA shape, measured on B200 (profiles/r02_direct_shapes.txt): two CTAs of 256 threads per SM beat one of 512 / 640 /
-// 768 -- the phases of a wave (stage B/F tasks, direct sums, finish) are separated by CTA barriers, and a second
-// CTA fills the FP64 pipe while the first one waits (+4.5 % normal equations, +32 % objective).
+// CTA shape, measured on B200 (profiles/r02_direct_shapes.txt): two CTAs per SM beat one of 512 / 640 / 768 threads --
+// the phases of a wave (stage B/F tasks, direct sums, finish) are separated by CTA barriers, and a second CTA fills the
+// FP64 pipe while the first one waits (256 x 2 against 512 x 1: +4.5 % normal equations, +32 % objective); 384 threads
+// per CTA (80 registers, ~300 B of spills, 24 warps per SM) add another 3 % over 256 (126 registers, 16 warps).
 #ifndef HB_DNT
-#define HB_DNT 256
+#define HB_DNT 384
 #endif
 #ifndef HB_DCAP
 #define HB_DCAP 448
 #endif
 #ifndef HB_DITEMS
-#define HB_DITEMS 256
+#define HB_DITEMS 384
 #endif
 #ifndef HB_DCTAS
 #define HB_DCTAS 2
@@ -53,10 +54,10 @@ constexpr int kDCtasPerSM = HB_DCTAS;
 constexpr int kDChunk = 64;       // points per chunk (one DFT item = chunk x pair)
 constexpr int kDMaxPairs = 64;    // conjugate pairs per maturity this kernel takes
 constexpr int kDMaxMat = 512;     // maturities per surface (prefix table in shared memory)
-constexpr int kDMaxCh = 96;       // chunks per wave
-constexpr int kDMaxSeg = 64;      // maturity pieces per wave
+constexpr int kDMaxCh = 64;       // chunks per wave
+constexpr int kDMaxSeg = 48;      // maturity pieces per wave
 constexpr int kDAFields = 5;      // stage-A cache: num, L0, d, g, q1
-constexpr int kDMapMax = 8192 / 32 + 1;  // coarse slot / item maps of a wave (CAP, ITEMS <= 8192)
+constexpr int kDMapMax = 4096 / 32 + 1;  // coarse slot / item maps of a wave (CAP, ITEMS <= 4096)
 
 struct DirectDev {
     const double2* tw;    // [2 n_full]  (cos, sin)(pi k / n_full)
@@ -203,23 +204,34 @@ __device__ __forceinline__ int direct_find(const int* start, const unsigned char
     return c;
 }
 
-// Prefix length of maturity m for class constants cc and the class's variants (kts[], v0s[] of nv variants):
-// 4 consecutive lanes share the scan over the bound's blocks, from the end of the grid downwards.
-__device__ __forceinline__ int direct_prefix(const PrefixBlock* blocks, const int* blk, int nblk, double T, double cst,
-                                             const double* kts, const double* v0s, int nv, double cut, int sub) {
-    int last_live = -1;
-    for (int k = nblk - 1 - sub; k >= 0; k -= 4) {
-        const PrefixTerms t = prefix_terms(blocks[k], T);  // shared by the variants of the class
-        bool dead = true;
-        for (int i = 0; i < nv; ++i) dead = dead && (prefix_ub_of(t, kts[i], v0s[i], cst) < cut - kPrefixMargin);
-        if (!dead) {
-            last_live = k;
-            break;
-        }
+// Prefix length of one (class, maturity): the start of the first block such that it and every later block is dead for
+// all nv variants of the class.  Two levels: super-blocks of kDSuper fine blocks (one bound over the merged range,
+// looser but valid) are scanned from the end of the grid first, then the fine blocks below the first live one.
+constexpr int kDSuper = 8;
+__device__ __forceinline__ int direct_nsuper(int nblk) { return (nblk + kDSuper - 1) / kDSuper; }
+__device__ __forceinline__ int direct_prefix(const PrefixBlock* fine, const PrefixBlock* super, const int* blk, int nblk,
+                                             double T, double cst, const double* kts, const double* v0s, int nv,
+                                             double cut) {
+    auto dead = [&](const PrefixBlock& b) -> bool {
+        const PrefixTerms t = prefix_terms(b, T);  // shared by the variants of the class
+        bool d = true;
+        for (int i = 0; i < nv; ++i) d = d && (prefix_ub_of(t, kts[i], v0s[i], cst) < cut - kPrefixMargin);
+        return d;
+    };
+    int k = nblk - 1;
+    for (int sb = direct_nsuper(nblk) - 1; sb >= 0; --sb) {
+        if (!dead(super[sb])) break;
+        k = kDSuper * sb - 1;
     }
-    last_live = max(last_live, __shfl_xor_sync(0xffffffffu, last_live, 1));
-    last_live = max(last_live, __shfl_xor_sync(0xffffffffu, last_live, 2));
-    return blk[last_live + 1];  // all blocks dead: blk[0] = 1 (point 0 is always evaluated)
+    for (; k >= 0; --k)
+        if (!dead(fine[k])) break;
+    return blk[k + 1];  // all blocks dead: blk[0] = 1 (point 0 is always evaluated)
+}
+// fine and super blocks of a class: entry i < nblk is fine block i, entry nblk + s super-block s
+__device__ __forceinline__ PrefixBlock direct_block_at(const PrefixClass& pc, const int* blk, int nblk, int i, double eta) {
+    if (i < nblk) return prefix_block(pc, eta * (double)blk[i], eta * (double)(blk[i + 1] - 1));
+    const int sb = i - nblk, k0 = kDSuper * sb, k1 = min(nblk, k0 + kDSuper);
+    return prefix_block(pc, eta * (double)blk[k0], eta * (double)(blk[k1] - 1));
 }
 
 template <bool ONEVAR>
@@ -309,18 +321,16 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
         if (D.jtab) {
             for (int m = m_begin + tid; m < m_end; m += NT) s_J[m] = D.jtab[(size_t)p * M + m];
         } else {
-            for (int i = tid; i < NCLS * D.nblk; i += NT) {
-                const int ci = i / D.nblk, k = i - ci * D.nblk;
+            const int nb2 = D.nblk + direct_nsuper(D.nblk);  // fine + super blocks per class
+            for (int i = tid; i < NCLS * nb2; i += NT) {
+                const int ci = i / nb2;
                 const PrefixClass pc = prefix_class(s_cc[ci], gc.alpha);
-                s_blocks[i] = prefix_block(pc, gc.eta * (double)D.blk[k], gc.eta * (double)(D.blk[k + 1] - 1));
+                s_blocks[i] = direct_block_at(pc, D.blk, D.nblk, i - ci * nb2, gc.eta);
             }
             __syncthreads();
             const int nm = m_end - m_begin;
-            for (int i0 = 0; i0 < NCLS * nm * 4; i0 += NT) {  // block-uniform trip count (shuffles inside)
-                const int i = i0 + tid;
-                const bool act = i < NCLS * nm * 4;
-                const int q = act ? i >> 2 : 0, sub = i & 3;
-                const int ci = q / nm, m = m_begin + (q - ci * nm);
+            for (int i = tid; i < NCLS * nm; i += NT) {  // one (class, maturity) per thread
+                const int ci = i / nm, m = m_begin + (i - ci * nm);
                 const double T = S.mat_T[m];
                 const double cst = -gc.ui * (S.ln_spot + (S.rate - S.dividend) * T);
                 double kts[3], v0s[3];
@@ -340,8 +350,9 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                     kts[0] = s_kts[v];
                     v0s[0] = s_v0s[v];
                 }
-                const int J = direct_prefix(s_blocks + (size_t)ci * D.nblk, D.blk, D.nblk, T, cst, kts, v0s, nv, gc.cut, sub);
-                if (act && sub == 0) atomicMax(&s_J[m], min(J, NF));
+                const PrefixBlock* fb = s_blocks + (size_t)ci * nb2;
+                const int J = direct_prefix(fb, fb + D.nblk, D.blk, D.nblk, T, cst, kts, v0s, nv, gc.cut);
+                atomicMax(&s_J[m], min(J, NF));
             }
             __syncthreads();
         }
@@ -605,7 +616,8 @@ prefix_scan_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const dou
     constexpr int V = ONEVAR ? 1 : 6, NCLS = ONEVAR ? 1 : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    PrefixBlock* blocks = reinterpret_cast<PrefixBlock*>(smem_raw) + (size_t)warp * D.nblk;  // one class at a time
+    const int nb2 = D.nblk + direct_nsuper(D.nblk);  // fine + super blocks of one class at a time
+    PrefixBlock* blocks = reinterpret_cast<PrefixBlock*>(smem_raw) + (size_t)warp * nb2;
     __shared__ JobState jss[kScanWarps];
     __shared__ double s_kts[kScanWarps][6], s_v0s[kScanWarps][6];
     __shared__ int s_jm[kScanWarps][kDMaxMat];
@@ -634,8 +646,7 @@ prefix_scan_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const dou
                 const double* xc = js.x[direct_cls_variant(ci)];
                 const ClassConst cc = {xc[0], xc[2] * xc[2], xc[3] * xc[2]};
                 const PrefixClass pc = prefix_class(cc, gc.alpha);
-                for (int k = lane; k < D.nblk; k += 32)
-                    blocks[k] = prefix_block(pc, gc.eta * (double)D.blk[k], gc.eta * (double)(D.blk[k + 1] - 1));
+                for (int k = lane; k < nb2; k += 32) blocks[k] = direct_block_at(pc, D.blk, D.nblk, k, gc.eta);
             }
             __syncwarp();
             double kts[3], v0s[3];
@@ -655,13 +666,11 @@ prefix_scan_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const dou
                 kts[0] = s_kts[warp][v];
                 v0s[0] = s_v0s[warp][v];
             }
-            for (int m0 = 0; m0 < M; m0 += 8) {  // 8 maturities x 4 lanes per round
-                const int m = m0 + (lane >> 2), sub = lane & 3;
-                const bool act = m < M;
-                const double T = S.mat_T[act ? m : 0];
+            for (int m = lane; m < M; m += 32) {  // one maturity per lane
+                const double T = S.mat_T[m];
                 const double cst = -gc.ui * (S.ln_spot + (S.rate - S.dividend) * T);
-                const int J = direct_prefix(blocks, D.blk, D.nblk, T, cst, kts, v0s, nv, gc.cut, sub);
-                if (act && sub == 0) s_jm[warp][m] = max(s_jm[warp][m], min(J, D.n_full));
+                const int J = direct_prefix(blocks, blocks + D.nblk, D.blk, D.nblk, T, cst, kts, v0s, nv, gc.cut);
+                s_jm[warp][m] = max(s_jm[warp][m], min(J, D.n_full));
             }
         }
         __syncwarp();

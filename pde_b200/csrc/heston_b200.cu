@@ -335,7 +335,7 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
             long_ids = short_ids + P;
             int* jtab = (int*)(rb + jt_off);
             HB_CUDA(cudaMemsetAsync(counts, 0, 256, st));
-            const size_t ssm = (size_t)kScanWarps * D.nblk * sizeof(PrefixBlock);
+            const size_t ssm = (size_t)kScanWarps * (D.nblk + (D.nblk + kDSuper - 1) / kDSuper) * sizeof(PrefixBlock);
             const int sgrid = std::min((P + kScanWarps - 1) / kScanWarps, 8 * max_ctas);
             const int pi_scan = prof_begin(0);
             if (one) {

@@ -51,7 +51,10 @@ namespace hb {
 #endif
 constexpr int kDNT = HB_DNT;      // threads per CTA
 constexpr int kDCtasPerSM = HB_DCTAS;
-constexpr int kDChunk = 64;       // points per chunk (one DFT item = chunk x pair)
+#ifndef HB_DCHUNK
+#define HB_DCHUNK 64
+#endif
+constexpr int kDChunk = HB_DCHUNK;  // points per chunk (one DFT item = chunk x pair)
 constexpr int kDMaxPairs = 64;    // conjugate pairs per maturity this kernel takes
 constexpr int kDMaxMat = 512;     // maturities per surface (prefix table in shared memory)
 constexpr int kDMaxCh = 64;       // chunks per wave

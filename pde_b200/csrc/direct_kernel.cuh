@@ -46,11 +46,24 @@ namespace hb {
 #ifndef HB_DCTAS
 #define HB_DCTAS 2
 #endif
+#ifndef HB_DNT1
+#define HB_DNT1 128
+#endif
+#ifndef HB_DCAP1
+#define HB_DCAP1 128
+#endif
+#ifndef HB_DITEMS1
+#define HB_DITEMS1 96
+#endif
+#ifndef HB_DCTAS1
+#define HB_DCTAS1 6
+#endif
+#ifndef HB_DPULL
+#define HB_DPULL 64  // K1 tasks per trip to the queue (32 or 64)
+#endif
 #ifndef HB_DPREFETCH
 #define HB_DPREFETCH 0
 #endif
-constexpr int kDNT = HB_DNT;      // threads per CTA
-constexpr int kDCtasPerSM = HB_DCTAS;
 #ifndef HB_DCHUNK
 #define HB_DCHUNK 64
 #endif
@@ -85,8 +98,12 @@ template <bool ONEVAR>
 struct DirectCfg {
     static constexpr int V = ONEVAR ? 1 : 6;
     static constexpr int NCLS = ONEVAR ? 1 : 4;
-    static constexpr int CAP = ONEVAR ? 4 * HB_DCAP : HB_DCAP;        // wave capacity in points
-    static constexpr int ITEMS = ONEVAR ? 4 * HB_DITEMS : HB_DITEMS;  // (chunk, pair) items per wave
+    // the one-variant kernel (prices, objective) holds 1/6 of the shared memory per point: six CTAs of 128 threads per SM
+    // measured +26 % over the six-variant kernel's shape (objective 49.5 -> 62.4 M slices/s; profiles/r02_negative_results.txt)
+    static constexpr int NT = ONEVAR ? HB_DNT1 : HB_DNT;       // threads per CTA
+    static constexpr int CTAS = ONEVAR ? HB_DCTAS1 : HB_DCTAS;  // CTAs per SM
+    static constexpr int CAP = ONEVAR ? 4 * HB_DCAP1 : HB_DCAP;        // wave capacity in points
+    static constexpr int ITEMS = ONEVAR ? 4 * HB_DITEMS1 : HB_DITEMS;  // (chunk, pair) items per wave
     static constexpr size_t smem_bytes() {
         return (size_t)V * CAP * 16 + (size_t)V * ITEMS * 16 + (size_t)2 * V * kDMaxPairs * 16;
     }
@@ -238,12 +255,12 @@ __device__ __forceinline__ PrefixBlock direct_block_at(const PrefixClass& pc, co
 }
 
 template <bool ONEVAR>
-__global__ void __launch_bounds__(kDNT, kDCtasPerSM)
+__global__ void __launch_bounds__(DirectCfg<ONEVAR>::NT, DirectCfg<ONEVAR>::CTAS)
 direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const double* __restrict__ params, int ld, int P,
                   int what, double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch,
                   int pieces, unsigned long long* job_counter) {
     using Cfg = DirectCfg<ONEVAR>;
-    constexpr int V = Cfg::V, NCLS = Cfg::NCLS, CAP = Cfg::CAP, ITEMS = Cfg::ITEMS, NT = kDNT;
+    constexpr int V = Cfg::V, NCLS = Cfg::NCLS, CAP = Cfg::CAP, ITEMS = Cfg::ITEMS, NT = Cfg::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* ybuf = reinterpret_cast<double2*>(smem_raw);  // [V][CAP]   z_j of the wave's points
     double2* part = ybuf + (size_t)V * CAP;                // [V][ITEMS] (P, Q) of every (chunk, pair)
@@ -398,8 +415,8 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                     i = first ? tid : i + NT;
                     if (i >= ntasks) break;
                 } else {  // blocks of 64 tasks: lane l takes tasks l and l + 32 of the block
-                    if (first || half) {
-                        if ((tid & 31) == 0) blk0 = atomicAdd(&s_task, 64);
+                    if (first || half || HB_DPULL == 32) {
+                        if ((tid & 31) == 0) blk0 = atomicAdd(&s_task, HB_DPULL);
                         blk0 = __shfl_sync(0xffffffffu, blk0, 0);
                         if (blk0 >= ntasks) break;
                         half = 0;

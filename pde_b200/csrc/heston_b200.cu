@@ -293,8 +293,8 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
     if (pl->mode == HB_MODE_FFT && direct_enabled() && pl->direct_ok && gc.cut >= kDirectMinCut) {
         // Live prefix + direct sums (direct_kernel.cuh).  Small batches are cut into pieces of maturities so that
         // every SM has work; the arithmetic of a maturity does not depend on the piece or wave it is priced in.
-        const int max_ctas = pl->sm_count * kDCtasPerSM;
         const bool one = (V == 1);
+        const int max_ctas = pl->sm_count * (one ? DirectCfg<true>::CTAS : DirectCfg<false>::CTAS);
         const bool groups_ok = M > 0;
         int pieces = 1;
         if (M > 1 && (long long)P < 2LL * max_ctas && (size_t)P * row_bytes <= (size_t(1) << 30))
@@ -358,11 +358,11 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
         const int pi_direct = prof_begin(1);
         if (one) {
             if ((rc = set_smem(direct_job_kernel<true>, DirectCfg<true>::smem_bytes()))) return rc;
-            direct_job_kernel<true><<<grid, kDNT, DirectCfg<true>::smem_bytes(), st>>>(
+            direct_job_kernel<true><<<grid, DirectCfg<true>::NT, DirectCfg<true>::smem_bytes(), st>>>(
                 S, D, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, pieces, ctr);
         } else {
             if ((rc = set_smem(direct_job_kernel<false>, DirectCfg<false>::smem_bytes()))) return rc;
-            direct_job_kernel<false><<<grid, kDNT, DirectCfg<false>::smem_bytes(), st>>>(
+            direct_job_kernel<false><<<grid, DirectCfg<false>::NT, DirectCfg<false>::smem_bytes(), st>>>(
                 S, D, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, pieces, ctr);
         }
         prof_end(pi_direct);
@@ -375,8 +375,9 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
                                  pieces > 1 ? 1 : 0, false, D.jtab)))
                 return rc;
             if (pieces > 1 && what != W_PRICE) {
-                finalize_rows_kernel<kDNT, kFinalizeT<kDNT>()><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
-                                                                                       scratch, d_out, d_out2);
+                // 256 threads: the summing threads of finalize_job in every Carr-Madan job kernel (kFinalizeT)
+                finalize_rows_kernel<256, 256><<<std::min(P, 4 * max_ctas), 256, 0, st>>>(S, pl->bd, d_params, ld, P, what, scratch,
+                                                                                         d_out, d_out2);
                 g_launches++;
                 HB_CUDA(cudaGetLastError());
             }
@@ -385,8 +386,8 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
         g_launches++;
         HB_CUDA(cudaGetLastError());
         if (pieces > 1 && what != W_PRICE) {
-            finalize_rows_kernel<kDNT, kFinalizeT<kDNT>()><<<std::min(P, 4 * max_ctas), kDNT, 0, st>>>(S, pl->bd, d_params, ld, P, what,
-                                                                                   scratch, d_out, d_out2);
+            finalize_rows_kernel<256, 256><<<std::min(P, 4 * max_ctas), 256, 0, st>>>(S, pl->bd, d_params, ld, P, what, scratch, d_out,
+                                                                                     d_out2);
             g_launches++;
             HB_CUDA(cudaGetLastError());
         }

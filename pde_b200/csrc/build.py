@@ -41,7 +41,7 @@ def needs_build() -> bool:
 
 # every elision of the fused kernel off: no perturbed-class tail skip, no asymptotic / series stage B, no rigorous
 # tail bound in the decimation path (run it with hb_plan_set_truncation(plan, 0) for "exact" underflow-only zeros)
-NOELIDE_DEFINES = ["HB_TAIL=0", "HB_ASYM_DT=1e300", "HB_MID=0", "HB_BOUND_DECIM=0", "HB_ZERO_AWARE=0"]
+NOELIDE_DEFINES = ["HB_TAIL=0", "HB_ASYM_DT=1e300", "HB_MID=0", "HB_BOUND_DECIM=0", "HB_ZERO_AWARE=0", "HB_F3_PERT=0"]
 
 
 def build_variant(name: str, defines, verbose: bool = False) -> str:

@@ -47,16 +47,16 @@ namespace hb {
 #define HB_DCTAS 2
 #endif
 #ifndef HB_DNT1
-#define HB_DNT1 128
+#define HB_DNT1 256
 #endif
 #ifndef HB_DCAP1
-#define HB_DCAP1 128
+#define HB_DCAP1 256
 #endif
 #ifndef HB_DITEMS1
-#define HB_DITEMS1 96
+#define HB_DITEMS1 192
 #endif
 #ifndef HB_DCTAS1
-#define HB_DCTAS1 6
+#define HB_DCTAS1 4
 #endif
 #ifndef HB_DPULL
 #define HB_DPULL 64  // K1 tasks per trip to the queue (32 or 64)
@@ -98,14 +98,18 @@ template <bool ONEVAR>
 struct DirectCfg {
     static constexpr int V = ONEVAR ? 1 : 6;
     static constexpr int NCLS = ONEVAR ? 1 : 4;
-    // the one-variant kernel (prices, objective) holds 1/6 of the shared memory per point: six CTAs of 128 threads per SM
-    // measured +26 % over the six-variant kernel's shape (objective 49.5 -> 62.4 M slices/s; profiles/r02_negative_results.txt)
+    // the one-variant kernel (prices, objective) holds 1/6 of the shared memory per point: four CTAs of 256 threads per SM
+    // measured +24 % over the six-variant kernel's shape (objective 49.5 -> 61.3 M slices/s; 128 x 6 gives 62.4 M but its
+    // finalize would sum over 128 threads: the loss column of the normal equations must equal the objective's bit for bit)
     static constexpr int NT = ONEVAR ? HB_DNT1 : HB_DNT;       // threads per CTA
     static constexpr int CTAS = ONEVAR ? HB_DCTAS1 : HB_DCTAS;  // CTAs per SM
     static constexpr int CAP = ONEVAR ? 4 * HB_DCAP1 : HB_DCAP;        // wave capacity in points
     static constexpr int ITEMS = ONEVAR ? 4 * HB_DITEMS1 : HB_DITEMS;  // (chunk, pair) items per wave
-    static constexpr size_t smem_bytes() {
-        return (size_t)V * CAP * 16 + (size_t)V * ITEMS * 16 + (size_t)2 * V * kDMaxPairs * 16;
+    // nblk: blocks of the prefix bound (the block table of an unrouted launch aliases the wave buffers)
+    static constexpr size_t smem_bytes(int nblk = 0) {
+        const size_t buffers = (size_t)V * CAP * 16 + (size_t)V * ITEMS * 16 + (size_t)2 * V * kDMaxPairs * 16;
+        const size_t blocks = (size_t)NCLS * (nblk + (nblk + 7) / 8) * sizeof(PrefixBlock);
+        return buffers > blocks ? buffers : blocks;
     }
 };
 
@@ -261,6 +265,7 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                   int pieces, unsigned long long* job_counter) {
     using Cfg = DirectCfg<ONEVAR>;
     constexpr int V = Cfg::V, NCLS = Cfg::NCLS, CAP = Cfg::CAP, ITEMS = Cfg::ITEMS, NT = Cfg::NT;
+    static_assert(kFinalizeT<NT>() == 256, "every Carr-Madan job kernel sums its finalize over 256 threads (same bits)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* ybuf = reinterpret_cast<double2*>(smem_raw);  // [V][CAP]   z_j of the wave's points
     double2* part = ybuf + (size_t)V * CAP;                // [V][ITEMS] (P, Q) of every (chunk, pair)
@@ -480,34 +485,8 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                     }
                     double pr[3] = {0.0, 0.0, 0.0}, pi[3] = {0.0, 0.0, 0.0};
                     if (!(er[0] < gc.cut && er[1] < gc.cut && er[2] < gc.cut)) {
-                        // theta' and v0' move the exponent by dl = dkts B + dv0s Dq, ~1e-8 |B|: where |dl| <= 2^-17
-                        // phi' = phi e^{dl} = phi (1 + dl + dl^2/2 + dl^3/6) to 1e-22 relative -- one cexp instead of
-                        // three, and dl is formed from the exact parameter differences, so phi' - phi (what the
-                        // finite difference reads) carries less rounding than two separate exponentials would
-                        cplx dl[3];
-                        bool small = true;
-#pragma unroll
-                        for (int g = 1; g < 3; ++g) {
-                            const double dk = s_kts[vs[g]] - s_kts[0], dv = s_v0s[vs[g]] - s_v0s[0];
-                            dl[g] = {fma(dk, b.B.re, dv * b.Dq.re), fma(dk, b.B.im, dv * b.Dq.im)};
-                            small = small && (fma(dl[g].re, dl[g].re, dl[g].im * dl[g].im) <= 5.8e-11);
-                        }
-                        if (small) {
-                            cexp_w<1>(er, ei, pr, pi);
-                            const cplx phi = {pr[0], pi[0]};
-#pragma unroll
-                            for (int g = 1; g < 3; ++g) {
-                                cplx t = {fma(dl[g].re, 1.0 / 3.0, 1.0), dl[g].im * (1.0 / 3.0)};   // 1 + dl/3
-                                t = cmul(dl[g], t);
-                                t = {fma(t.re, 0.5, 1.0), t.im * 0.5};                            // 1 + dl/2 (1 + dl/3)
-                                t = cmul(dl[g], t);                                              // e^{dl} - 1
-                                const cplx u = cmul(phi, t);
-                                pr[g] = phi.re + u.re;
-                                pi[g] = phi.im + u.im;
-                            }
-                        } else {
-                            cexp_w<3>(er, ei, pr, pi);
-                        }
+                        const double ks[3] = {s_kts[0], s_kts[2], s_kts[5]}, vs3[3] = {s_v0s[0], s_v0s[2], s_v0s[5]};
+                        class0_cexp(er, ei, b, ks, vs3, pr, pi);  // one cexp + two expansions where the steps are small
                     }
 #pragma unroll
                     for (int g = 0; g < 3; ++g) {

@@ -357,12 +357,12 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
         }
         const int pi_direct = prof_begin(1);
         if (one) {
-            if ((rc = set_smem(direct_job_kernel<true>, DirectCfg<true>::smem_bytes()))) return rc;
-            direct_job_kernel<true><<<grid, DirectCfg<true>::NT, DirectCfg<true>::smem_bytes(), st>>>(
+            if ((rc = set_smem(direct_job_kernel<true>, DirectCfg<true>::smem_bytes(pl->D.nblk)))) return rc;
+            direct_job_kernel<true><<<grid, DirectCfg<true>::NT, DirectCfg<true>::smem_bytes(pl->D.nblk), st>>>(
                 S, D, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, pieces, ctr);
         } else {
-            if ((rc = set_smem(direct_job_kernel<false>, DirectCfg<false>::smem_bytes()))) return rc;
-            direct_job_kernel<false><<<grid, DirectCfg<false>::NT, DirectCfg<false>::smem_bytes(), st>>>(
+            if ((rc = set_smem(direct_job_kernel<false>, DirectCfg<false>::smem_bytes(pl->D.nblk)))) return rc;
+            direct_job_kernel<false><<<grid, DirectCfg<false>::NT, DirectCfg<false>::smem_bytes(pl->D.nblk), st>>>(
                 S, D, gc, pl->bd, d_params, ld, P, what, d_out, d_out2, scratch, pieces, ctr);
         }
         prof_end(pi_direct);

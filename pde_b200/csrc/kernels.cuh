@@ -351,6 +351,39 @@ __device__ __forceinline__ double finish_price(double call, bool is_call, double
     return (put < 0.0) ? 0.0 : put;
 }
 
+// The three final exponentials of a class-0 point (base, theta', v0': same stage B).  theta' and v0' move the exponent
+// by dl = dkts B + dv0s Dq, ~1e-8 |B|: where |dl| <= 2^-17, phi' = phi e^{dl} = phi (1 + dl + dl^2/2 + dl^3/6) to 1e-22
+// relative -- one cexp instead of three, and dl is formed from the exact parameter differences, so phi' - phi (what the
+// finite difference reads) carries less rounding than two separate exponentials would.  Otherwise (finite-difference
+// steps limited by a bound, NaN) the three full exponentials.  kts / v0s: of the three variants, base first.
+__device__ __forceinline__ void class0_cexp(const double* er, const double* ei, const StageB& b, const double* kts,
+                                            const double* v0s, double* pr, double* pi) {
+    cplx dl[3];
+    bool small = true;
+#pragma unroll
+    for (int g = 1; g < 3; ++g) {
+        const double dk = kts[g] - kts[0], dv = v0s[g] - v0s[0];
+        dl[g] = {fma(dk, b.B.re, dv * b.Dq.re), fma(dk, b.B.im, dv * b.Dq.im)};
+        small = small && (fma(dl[g].re, dl[g].re, dl[g].im * dl[g].im) <= 5.8e-11);
+    }
+    if (small) {
+        cexp_w<1>(er, ei, pr, pi);
+        const cplx phi = {pr[0], pi[0]};
+#pragma unroll
+        for (int g = 1; g < 3; ++g) {
+            cplx t = {fma(dl[g].re, 1.0 / 3.0, 1.0), dl[g].im * (1.0 / 3.0)};  // 1 + dl/3
+            t = cmul(dl[g], t);
+            t = {fma(t.re, 0.5, 1.0), t.im * 0.5};                             // 1 + dl/2 (1 + dl/3)
+            t = cmul(dl[g], t);                                               // e^{dl} - 1
+            const cplx u = cmul(phi, t);
+            pr[g] = phi.re + u.re;
+            pi[g] = phi.im + u.im;
+        }
+    } else {
+        cexp_w<3>(er, ei, pr, pi);
+    }
+}
+
 // ============================================================================================
 // Fused Carr-Madan FFT job kernel
 // ============================================================================================
@@ -425,6 +458,9 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
 #endif
 #ifndef HB_F3
 #define HB_F3 1
+#endif
+#ifndef HB_F3_PERT
+#define HB_F3_PERT 1  // class-0 variants by expansion around the base exponential (class0_cexp)
 #endif
 #ifndef HB_TAIL
 #define HB_TAIL 1
@@ -721,7 +757,15 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
                         }
                         dmask |= (er[0] < gc.cut_dead ? 1u : 0u) << k;
                         double pr[3] = {0.0, 0.0, 0.0}, pi[3] = {0.0, 0.0, 0.0};
-                        if (!(er[0] < gc.cut && er[1] < gc.cut && er[2] < gc.cut)) cexp_w<3>(er, ei, pr, pi);
+                        if (!(er[0] < gc.cut && er[1] < gc.cut && er[2] < gc.cut)) {
+#if HB_F3_PERT
+                            const double ks[3] = {grp.s[0].kts, grp.s[1].kts, grp.s[2].kts};
+                            const double vs3[3] = {grp.s[0].v0s, grp.s[1].v0s, grp.s[2].v0s};
+                            class0_cexp(er, ei, b, ks, vs3, pr, pi);
+#else
+                            cexp_w<3>(er, ei, pr, pi);
+#endif
+                        }
 #pragma unroll
                         for (int g = 0; g < 3; ++g) {
                             const bool zero = er[g] < gc.cut;  // exactly 0 as in stage_f

@@ -68,7 +68,8 @@ namespace hb {
 #define HB_DCHUNK 64
 #endif
 constexpr int kDChunk = HB_DCHUNK;  // points per chunk (one DFT item = chunk x pair)
-constexpr int kDMaxPairs = 64;    // conjugate pairs per maturity this kernel takes
+constexpr int kDMaxPairs = 64;    // conjugate pairs per maturity the six-variant kernel takes
+constexpr int kDMaxPairs1 = 256;  // ... the one-variant kernel (1/6 of the shared memory per pair: config 5's 200 strikes fit)
 constexpr int kDMaxMat = 512;     // maturities per surface (prefix table in shared memory)
 constexpr int kDMaxCh = 64;       // chunks per wave
 constexpr int kDMaxSeg = 48;      // maturity pieces per wave
@@ -92,6 +93,7 @@ struct DirectDev {
     const int* job_ids;   // optional: the parameter sets this launch prices (null = 0..P-1)
     const int* jtab;      // optional [P][n_mat]: prefix lengths precomputed by prefix_scan_kernel (null = compute here)
     const int* p_count;   // optional: number of entries of job_ids, written on the device by prefix_scan_kernel
+    int max_pairs;        // most conjugate pairs any maturity of the surface has
 };
 
 template <bool ONEVAR>
@@ -103,11 +105,12 @@ struct DirectCfg {
     // finalize would sum over 128 threads: the loss column of the normal equations must equal the objective's bit for bit)
     static constexpr int NT = ONEVAR ? HB_DNT1 : HB_DNT;       // threads per CTA
     static constexpr int CTAS = ONEVAR ? HB_DCTAS1 : HB_DCTAS;  // CTAs per SM
+    static constexpr int MAXP = ONEVAR ? kDMaxPairs1 : kDMaxPairs;      // conjugate pairs per maturity
     static constexpr int CAP = ONEVAR ? 4 * HB_DCAP1 : HB_DCAP;        // wave capacity in points
     static constexpr int ITEMS = ONEVAR ? 4 * HB_DITEMS1 : HB_DITEMS;  // (chunk, pair) items per wave
     // nblk: blocks of the prefix bound (the block table of an unrouted launch aliases the wave buffers)
     static constexpr size_t smem_bytes(int nblk = 0) {
-        const size_t buffers = (size_t)V * CAP * 16 + (size_t)V * ITEMS * 16 + (size_t)2 * V * kDMaxPairs * 16;
+        const size_t buffers = (size_t)V * CAP * 16 + (size_t)V * ITEMS * 16 + (size_t)2 * V * MAXP * 16;
         const size_t blocks = (size_t)NCLS * (nblk + (nblk + 7) / 8) * sizeof(PrefixBlock);
         return buffers > blocks ? buffers : blocks;
     }
@@ -264,12 +267,13 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                   int what, double* __restrict__ out, double* __restrict__ out2, double* __restrict__ scratch,
                   int pieces, unsigned long long* job_counter) {
     using Cfg = DirectCfg<ONEVAR>;
-    constexpr int V = Cfg::V, NCLS = Cfg::NCLS, CAP = Cfg::CAP, ITEMS = Cfg::ITEMS, NT = Cfg::NT;
+    constexpr int V = Cfg::V, NCLS = Cfg::NCLS, CAP = Cfg::CAP, ITEMS = Cfg::ITEMS, NT = Cfg::NT, MAXP = Cfg::MAXP;
+    static_assert(ITEMS >= MAXP, "a wave holds at least one chunk of the widest maturity");
     static_assert(kFinalizeT<NT>() == 256, "every Carr-Madan job kernel sums its finalize over 256 threads (same bits)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* ybuf = reinterpret_cast<double2*>(smem_raw);  // [V][CAP]   z_j of the wave's points
     double2* part = ybuf + (size_t)V * CAP;                // [V][ITEMS] (P, Q) of every (chunk, pair)
-    // [2][V][kDMaxPairs] running sums of a maturity cut by a wave; by wave parity: the first piece of a wave may read
+    // [2][V][MAXP] running sums of a maturity cut by a wave; by wave parity: the first piece of a wave may read
     // the sums its predecessor left while the last piece of the same wave leaves its own
     double2* carry = part + (size_t)V * ITEMS;
     PrefixBlock* s_blocks = reinterpret_cast<PrefixBlock*>(smem_raw);  // [NCLS][nblk], job set-up only (aliases ybuf)
@@ -305,7 +309,7 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
 #ifdef HB_DBG_POISON
         {  // diagnostic build: anything read before it is written shows up as NaN
             const double2 nan2 = make_double2(__longlong_as_double(0x7ff8000000000000LL), __longlong_as_double(0x7ff8000000000000LL));
-            for (int i = tid; i < V * CAP + V * ITEMS + 2 * V * kDMaxPairs; i += NT) ybuf[i] = nan2;
+            for (int i = tid; i < V * CAP + V * ITEMS + 2 * V * MAXP; i += NT) ybuf[i] = nan2;
             for (int i = tid; i < NCLS * kDAFields * NF; i += NT) acache[i] = nan2;
         }
         __syncthreads();
@@ -414,7 +418,10 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
             // ---- K1: one task = (class, point of a maturity): stage B, then stage F of the class's variants ----
             // Tasks differ in cost (class 0 carries three final cexps, low grid points the full stage B): warps pull
             // blocks of 32 tasks from a queue, class 0 first.
-            const int ntasks = NCLS * nslots;
+#ifndef HB_DBG_NOK1
+#define HB_DBG_NOK1 0
+#endif
+            const int ntasks = HB_DBG_NOK1 ? 0 : NCLS * nslots;
             for (int i = ntasks, first = 1, half = 0, blk0 = 0;; first = 0) {
                 if (ONEVAR) {  // uniform tasks: static assignment
                     i = first ? tid : i + NT;
@@ -505,7 +512,10 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
             // every warp has left K1 and none re-enters it before the next barrier: reset the task queue here
             if (tid == 0) s_task = 0;
             // ---- direct sums: item = (chunk, conjugate pair), all V slices ----
-            for (int it = tid; it < nitems; it += NT) {
+#ifndef HB_DBG_NODFT
+#define HB_DBG_NODFT 0
+#endif
+            for (int it = tid; it < (HB_DBG_NODFT ? 0 : nitems); it += NT) {
                 const int c = direct_find(w.c_item0, w.imap, it);
                 const int m = w.c_mat[c], pi_ = it - w.c_item0[c];
                 const unsigned d2 = (unsigned)D.pair_d2[D.pair_off[m] + pi_];
@@ -550,10 +560,10 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
             // `carry` (by wave parity: the first piece of a wave may read what its predecessor left while the last
             // piece leaves its own).  No barrier up to the next K1: that one only writes ybuf. ----
             {
-                const double2* carry_in = carry + (size_t)(wi & 1) * V * kDMaxPairs;
-                double2* carry_out = carry + (size_t)((wi + 1) & 1) * V * kDMaxPairs;
+                const double2* carry_in = carry + (size_t)(wi & 1) * V * MAXP;
+                double2* carry_out = carry + (size_t)((wi + 1) & 1) * V * MAXP;
                 auto pair_sum = [&](int sg, int v, int pi_) -> double2 {
-                    double2 acc = (w.s_flags[sg] & 1) ? make_double2(0.0, 0.0) : carry_in[v * kDMaxPairs + pi_];
+                    double2 acc = (w.s_flags[sg] & 1) ? make_double2(0.0, 0.0) : carry_in[v * MAXP + pi_];
                     for (int cc = w.s_c0[sg]; cc < w.s_c1[sg]; ++cc) {
                         const double2 q = part[(size_t)v * ITEMS + w.c_item0[cc] + pi_];
                         acc.x += q.x;
@@ -562,7 +572,10 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                     return acc;
                 };
                 // tasks of all pieces flattened: (slice v, option) of an ending piece, (slice v, pair) of a cut one
-                const int ntask = w.s_t0[w.nseg];
+#ifndef HB_DBG_NOFIN
+#define HB_DBG_NOFIN 0
+#endif
+                const int ntask = HB_DBG_NOFIN ? 0 : w.s_t0[w.nseg];
                 for (int i = tid; i < V * ntask; i += NT) {
                     int v = 0, t = i;
                     if (V > 1) {
@@ -574,14 +587,14 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                     t -= w.s_t0[sg];
                     const int m = w.s_mat[sg];
                     if (!(w.s_flags[sg] & 2)) {  // only the last piece of a wave: keep the running sums
-                        carry_out[v * kDMaxPairs + t] = pair_sum(sg, v, t);
+                        carry_out[v * MAXP + t] = pair_sum(sg, v, t);
                         continue;
                     }
                     const int o = S.mat_off[m] + t;
                     const int q0 = D.opt_pq0[o], q1 = D.opt_pq1[o];
                     double price = __longlong_as_double(0x7ff8000000000000LL);
                     if (q0 >= 0) {
-                        HB_ASSERT((q0 >> 1) < kDMaxPairs && (q1 >> 1) < kDMaxPairs);
+                        HB_ASSERT((q0 >> 1) < MAXP && (q1 >> 1) < MAXP);
                         const double2 a0 = pair_sum(sg, v, q0 >> 1), a1 = pair_sum(sg, v, q1 >> 1);
                         const double x0 = (q0 & 1) ? a0.x + a0.y : a0.x - a0.y;
                         const double x1 = (q1 & 1) ? a1.x + a1.y : a1.x - a1.y;

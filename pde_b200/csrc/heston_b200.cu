@@ -290,7 +290,8 @@ int launch_jobs_impl(hb_plan* pl, const double* d_params, int ld, int P, int wha
         prof_end(pi_fft);
         return HB_OK;
     };
-    if (pl->mode == HB_MODE_FFT && direct_enabled() && pl->direct_ok && gc.cut >= kDirectMinCut) {
+    if (pl->mode == HB_MODE_FFT && direct_enabled() && pl->direct_ok && gc.cut >= kDirectMinCut &&
+        pl->D.max_pairs <= (V == 1 ? kDMaxPairs1 : kDMaxPairs)) {
         // Live prefix + direct sums (direct_kernel.cuh).  Small batches are cut into pieces of maturities so that
         // every SM has work; the arithmetic of a maturity does not depend on the piece or wave it is priced in.
         const bool one = (V == 1);
@@ -966,7 +967,8 @@ int hb_surface_set(hb_plan* pl, int n_opt, const double* strike, const double* m
     pl->D.pair_d2 = (const int*)(base + o_pd);
     pl->D.opt_pq0 = (const int*)(base + o_q0);
     pl->D.opt_pq1 = (const int*)(base + o_q1);
-    pl->direct_ok = pl->mode == HB_MODE_FFT && max_pairs <= kDMaxPairs && M <= kDMaxMat;
+    pl->direct_ok = pl->mode == HB_MODE_FFT && max_pairs <= kDMaxPairs1 && M <= kDMaxMat;
+    pl->D.max_pairs = max_pairs;
     pl->d_strike = (const double*)(base + o_K);
     pl->d_maturity = (const double*)(base + o_Tm);
     pl->d_is_call = (const uint8_t*)(base + o_ic);

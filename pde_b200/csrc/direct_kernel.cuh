@@ -394,7 +394,10 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
         __syncthreads();  // also: the prefix blocks (aliasing ybuf) have been read for the last time
         // ---- stage A (+ L0 of the asymptotic stage B) once per (class, point of the longest prefix) ----
         {
-            const int jall = s_jall;
+#ifndef HB_DBG_NOFILL
+#define HB_DBG_NOFILL 0
+#endif
+            const int jall = HB_DBG_NOFILL ? 0 : s_jall;
             for (int i = tid; i < NCLS * jall; i += NT) {
                 const int ci = i / jall, j = i - ci * jall;
                 const StageA a = stage_a(s_cc[ci], gc.eta * (double)j, gc.ui);
@@ -611,7 +614,10 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
             if (!w.more) break;
         }
         __syncthreads();  // the price rows of the job are complete
-        if (pieces == 1) finalize_job<NT, kFinalizeT<NT>()>(what, rows, S, js, p, out, out2, red, tid);
+#ifndef HB_DBG_NOFINAL
+#define HB_DBG_NOFINAL 0
+#endif
+        if (pieces == 1 && !HB_DBG_NOFINAL) finalize_job<NT, kFinalizeT<NT>()>(what, rows, S, js, p, out, out2, red, tid);
     }
 }
 

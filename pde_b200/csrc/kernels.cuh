@@ -125,6 +125,7 @@ struct Group {
 struct JobState {
     double x[6][5];
     double dx[5];
+    double rdx[5];  // 1 / dx
     int valid;
 };
 
@@ -164,6 +165,7 @@ __device__ __forceinline__ void job_setup(JobState& js, const double* params, in
             const double x1 = x[c] + h;
             js.x[c + 1][c] = x1;
             js.dx[c] = x1 - x[c];  // (x0 + h) - x0, as _dense_difference does
+            js.rdx[c] = 1.0 / js.dx[c];
         }
     }
 }
@@ -249,9 +251,11 @@ template <int NT>
 __host__ __device__ constexpr int kFinalizeT() { return NT >= 256 ? 256 : NT; }
 
 // _compute_residuals, heston_calibrator.py:533-535 (np.maximum propagates NaN)
-__device__ __forceinline__ double residual_of(double price, double mkt) {
+// One division per option (1 / market) and one per parameter and job (1 / dx) instead of twelve per option: the
+// residual (p - m) (1/m) is within 1.5 ulp of the reference's (p - m)/m.
+__device__ __forceinline__ double residual_of(double price, double mkt, double rmkt) {
     const double p = (price != price) ? price : fmax(price, 1e-10);
-    return (p - mkt) / mkt;
+    return (p - mkt) * rmkt;
 }
 
 // Turn the price rows of one job into the requested output.  rows[v * n_opt + i].
@@ -268,7 +272,7 @@ __device__ __forceinline__ void finalize_job(int what, const double* rows, const
             if (pr != pr || pr <= 0.0) {
                 acc[1] += 1.0;  // heston_calibrator.py:507-508
             } else {
-                const double e = (pr - m) / m;
+                const double e = (pr - m) * (1.0 / m);
                 acc[0] += e * e;
             }
         }
@@ -278,13 +282,13 @@ __device__ __forceinline__ void finalize_job(int what, const double* rows, const
     }
     if (what == W_JAC) {
         for (int i = tid; i < n; i += NT) {
-            const double m = S.mkt_orig[i];
-            const double r0 = residual_of(rows[i], m);
+            const double m = S.mkt_orig[i], rm = 1.0 / m;
+            const double r0 = residual_of(rows[i], m, rm);
             out[(size_t)p * n + i] = r0;
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
-                const double rc = residual_of(rows[(size_t)(c + 1) * n + i], m);
-                out2[((size_t)p * n + i) * 5 + c] = (rc - r0) / js.dx[c];
+                const double rc = residual_of(rows[(size_t)(c + 1) * n + i], m, rm);
+                out2[((size_t)p * n + i) * 5 + c] = (rc - r0) * js.rdx[c];
             }
         }
         return;
@@ -294,17 +298,17 @@ __device__ __forceinline__ void finalize_job(int what, const double* rows, const
 #pragma unroll
     for (int i = 0; i < 23; ++i) acc[i] = 0.0;
     for (int i = tid; i < n && tid < FT; i += FT) {
-        const double pr = rows[i], m = S.mkt_orig[i];
+        const double pr = rows[i], m = S.mkt_orig[i], rm = 1.0 / m;
         if (pr != pr || pr <= 0.0) {
             acc[22] += 1.0;
         } else {
-            const double e = (pr - m) / m;
+            const double e = (pr - m) * rm;
             acc[0] += e * e;
         }
-        const double r0 = residual_of(pr, m);
+        const double r0 = residual_of(pr, m, rm);
         double J[5];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) J[c] = (residual_of(rows[(size_t)(c + 1) * n + i], m) - r0) / js.dx[c];
+        for (int c = 0; c < 5; ++c) J[c] = (residual_of(rows[(size_t)(c + 1) * n + i], m, rm) - r0) * js.rdx[c];
         acc[1] += r0 * r0;
         int t = 7;
 #pragma unroll

@@ -30,7 +30,7 @@ def _viol(got, want):
 
 
 @pytest.mark.parametrize("n_grid,eta", [(16384, 0.25), (16384, 0.0625), (8192, 0.125), (32768, 0.05)])
-def test_fine_grid_prices_match_oracle(oracle, n_grid, eta):
+def test_fine_grid_prices_match_oracle(oracle, monkeypatch, n_grid, eta):
     import torch
 
     from pde_b200 import BatchPricer
@@ -41,10 +41,15 @@ def test_fine_grid_prices_match_oracle(oracle, n_grid, eta):
     params = _sets(7, seed=n_grid)
     params = params[params[:, 2] >= 0.02]  # keep the sigma ~ 0.01 corner for test_gpu_parity (4x tolerance there)
     pr = BatchPricer("fft", n_grid=n_grid, eta=eta).set_surface(K, T, ic, None, S0=S0, r=R, q=Q)
-    got = pr.price(torch.tensor(params, device="cuda:0")).cpu().numpy()
     want = oracle.price_batch(MODE_FFT, params, K, T, ic, S0, R, Q, N=n_grid, eta=eta)
-    for i in range(len(params)):
-        assert _viol(got[i], want[i]) <= 1.0, (i, params[i], _viol(got[i], want[i]))
+    # default dispatch (the one-variant direct-sum kernel where a maturity has <= 256 conjugate pairs: every case but
+    # the first) and the transform kernel with decimation in time forced (HB_DIRECT=0)
+    for force_transform in (False, True):
+        if force_transform:
+            monkeypatch.setenv("HB_DIRECT", "0")
+        got = pr.price(torch.tensor(params, device="cuda:0")).cpu().numpy()
+        for i in range(len(params)):
+            assert _viol(got[i], want[i]) <= 1.0, (force_transform, i, params[i], _viol(got[i], want[i]))
 
 
 def test_config5_shape_objective_and_normal_equations(oracle):

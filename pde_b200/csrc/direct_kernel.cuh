@@ -199,6 +199,7 @@ __device__ void direct_build_wave(DirectWave& w, const int* s_J, const SurfaceDe
             break;  // wave full
         }
     }
+    HB_ASSERT(nch <= kDMaxCh && nseg <= kDMaxSeg && nslots <= CAP && nitems <= ITEMS);
     w.c_slot0[nch] = nslots;
     w.c_item0[nch] = nitems;
     w.s_t0[0] = 0;
@@ -459,7 +460,8 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                 const int ci = (i >= nslots) + (i >= 2 * nslots) + (i >= 3 * nslots), slot = i - ci * nslots;
                 const int c = direct_find(w.c_slot0, w.smap, slot);
                 const int m = w.c_mat[c], j = w.c_j0[c] + (slot - w.c_slot0[c]);
-                HB_ASSERT(c >= 0 && c < nch && j >= 0 && j < NF && slot < CAP);
+                HB_ASSERT(c >= 0 && c < nch && j >= 0 && j < NF && slot >= 0 && slot < CAP && j < s_jall && j < s_J[m] &&
+                          ci >= 0 && ci < NCLS && slot - w.c_slot0[c] < w.c_len[c]);
                 const double T = w.c_T[c], lsm = w.c_lsm[c];
                 const double v = gc.eta * (double)j;
                 StageA a;
@@ -530,6 +532,8 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                 double aP[V], aQ[V];
 #pragma unroll
                 for (int v = 0; v < V; ++v) aP[v] = aQ[v] = 0.0;
+                HB_ASSERT(c >= 0 && c < nch && it < ITEMS && pi_ >= 0 && pi_ < MAXP && len >= 1 && len <= kDChunk &&
+                          w.c_slot0[c] + len <= CAP && pi_ < D.pair_off[m + 1] - D.pair_off[m]);
                 const double2* yb = ybuf + w.c_slot0[c];
                 int k = 0;
                 for (; k + 1 < len; k += 2) {
@@ -567,7 +571,9 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                 double2* carry_out = carry + (size_t)((wi + 1) & 1) * V * MAXP;
                 auto pair_sum = [&](int sg, int v, int pi_) -> double2 {
                     double2 acc = (w.s_flags[sg] & 1) ? make_double2(0.0, 0.0) : carry_in[v * MAXP + pi_];
+                    HB_ASSERT(sg >= 0 && sg < w.nseg && v >= 0 && v < V && pi_ >= 0 && pi_ < MAXP && w.s_c1[sg] <= w.nch);
                     for (int cc = w.s_c0[sg]; cc < w.s_c1[sg]; ++cc) {
+                        HB_ASSERT(w.c_item0[cc] + pi_ < w.c_item0[cc + 1] && w.c_item0[cc] + pi_ < ITEMS);
                         const double2 q = part[(size_t)v * ITEMS + w.c_item0[cc] + pi_];
                         acc.x += q.x;
                         acc.y += q.y;
@@ -605,6 +611,7 @@ direct_job_kernel(SurfaceDev S, DirectDev D, GridConst gc, Bounds bd, const doub
                         const double call = S.mat_disc[m] * (c0 + (c1 - c0) * S.opt_frac[o]);
                         price = finish_price(call, S.opt_call[o] != 0, S.mat_fwd[m], S.opt_kdisc[o]);
                     }
+                    HB_ASSERT(o >= S.mat_off[m] && o < S.mat_off[m + 1] && S.opt_orig[o] >= 0 && S.opt_orig[o] < n);
                     rows[(size_t)v * n + S.opt_orig[o]] = price;
                 }
             }

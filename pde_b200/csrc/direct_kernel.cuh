@@ -19,11 +19,13 @@
 //     all six slices, so its twiddle (an exact table value advanced by a two-way interleaved recurrence over at most
 //     32 steps) is shared by twelve accumulators;
 //   * adds the chunk partials of a maturity in chunk order (fixed: the bits do not depend on how the waves were
-//     packed, on the launch path or on the rank), then interpolates / clamps / applies parity as K3 does.
-// Three CTA barriers per wave (~800 points x 6 slices) instead of three per group of three slices.
+//     packed, on the launch path, the CTA shape or the rank), then interpolates / clamps / applies parity as K3 does.
+// Two CTA barriers per wave (~400 points x 6 slices; the finish step of a wave overlaps the next wave's K1) instead of
+// three per group of three slices, and two or more CTAs per SM so that one CTA's barrier is another's compute.
 // Everything after the prices (residuals, SciPy forward differences, normal equations) is kernels.cuh's finalize.
-// Host dispatch (heston_b200.cu): FFT-mode plans with a significance cut, <= kDMaxPairs pairs per maturity; jobs
-// whose prefix is long (slow decay, exact mode) go to fft_job_kernel, which costs O(N log N) whatever the prefix.
+// Host dispatch (heston_b200.cu): FFT-mode plans with a significance cut, <= kDMaxPairs (six variants) / kDMaxPairs1
+// (one variant) pairs per maturity; prefix_scan_kernel below bounds the live prefix of every (set, maturity) first and
+// sends the sets whose prefix is long (slow decay) to fft_job_kernel, which costs O(N log N) whatever the prefix.
 #pragma once
 #include "kernels.cuh"
 #include "prefix_bound.cuh"

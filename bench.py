@@ -8,7 +8,8 @@ config 3, the batched calibration objective + finite-difference Jacobian (as J^T
 normal-equation blocks) over P = 65,536 parameter sets x 32 maturities x 50 strikes,
 N = 4096, eta = 0.25, alpha = 0.75, per GPU (weak scaling: every rank prices its own P sets;
 the only collective is the NCCL all-gather of the 22-double result rows).  One step = one
-launch of the fused kernel = P x 32 x (1 + 5) slice evaluations; `value` counts all six.
+hb_normal_eq call (prefix scan, direct-sum job kernel, transform job kernel: DESIGN.md 4.0) = P x 32 x (1 + 5) slice
+evaluations; `value` counts all six.
 
 Prints ONE JSON line (rank 0).  `--impl reference` instead times the reference's own CPU
 implementation (oracle/_ref = its heston.cpp compiled unmodified, OpenMP over options) on a

@@ -100,3 +100,30 @@ def test_direct_and_transform_kernels_agree(monkeypatch, seed, n_grid, eta, alph
         assert (np.abs(j1 - j0)[okj] <= bound[okj]).all(), (thr, float(np.max((np.abs(j1 - j0) / bound)[okj])))
         np.testing.assert_allclose(n1[fin, :2], n0[fin, :2], rtol=1e-10)
     pr.close()
+
+
+def test_maturity_entirely_off_the_grid(monkeypatch):
+    """A maturity none of whose strikes lies on the log-strike grid has no bins at all (a wave piece without chunks in
+    the direct-sum kernel): its options are NaN, the others are priced as usual, on both kernels and both launch paths."""
+    import torch
+
+    from pde_b200 import BatchPricer
+
+    n_grid, eta = 512, 0.5  # grid ends at ln K = pi/eta = 6.28: K = 535
+    K = np.array([90.0, 100.0, 110.0, 600.0, 700.0, 900.0, 95.0, 105.0])
+    T = np.array([0.5, 0.5, 0.5, 1.0, 1.0, 1.0, 2.0, 2.0])
+    pr = BatchPricer("fft", n_grid=n_grid, eta=eta).set_surface(K, T, True, None, S0=S0, r=R, q=Q)
+    for n_sets in (5, 700):
+        xs = _params(np.random.default_rng(n_sets), n_sets)
+        X = torch.tensor(xs, device="cuda:0")
+        got = pr.price(X).cpu().numpy()
+        monkeypatch.setenv("HB_DIRECT", "0")
+        ref = pr.price(X).cpu().numpy()
+        monkeypatch.delenv("HB_DIRECT")
+        valid = (xs[:, 0] > 0) & (np.abs(xs[:, 3]) < 1)
+        assert np.isnan(got[:, 3:6]).all() and np.isnan(got[~valid]).all()
+        assert np.isfinite(got[valid][:, [0, 1, 2, 6, 7]]).all()
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = np.isfinite(ref)
+        assert (np.abs(got - ref)[ok] <= 0.05 * (1e-10 * np.abs(ref[ok]) + 1e-12)).all()
+    pr.close()

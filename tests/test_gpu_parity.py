@@ -534,9 +534,10 @@ def test_full_size_objective_properties(torch_cuda, oracle):
 
 def test_full_size_normal_equations_properties(torch_cuda):
     """BASELINE.json config 3 at full size (65,536 sets x 32 maturities x 50 strikes, FD blocks): properties
-    that do not need the oracle.  The six-variant kernel (dead masks, cexp_w<3>) and the one-variant kernel
-    (rigorous tail bound) are different instantiations with different work elision: the loss column of the
-    normal equations must still be the objective's loss bit for bit."""
+    that do not need the oracle.  The six-variant and the one-variant job kernels are different instantiations with
+    different CTA shapes, wave capacities and work elision (and a set may be routed to the direct-sum kernel by one and
+    to the transform kernel by the other only if their live-prefix tables differ): the loss column of the normal
+    equations must still be the objective's loss bit for bit."""
     from pde_b200 import BatchPricer
 
     torch = torch_cuda

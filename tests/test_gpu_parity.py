@@ -553,8 +553,12 @@ def test_full_size_normal_equations_properties(torch_cuda):
     a, b = neq[:, 0].cpu().numpy(), loss.cpu().numpy()
     assert np.array_equal(np.isfinite(a), np.isfinite(b)) and np.array_equal(a == 1e10, b == 1e10)
     ok = np.isfinite(a)
-    dev = np.max(np.abs(a[ok] - b[ok]) / np.abs(b[ok]))
-    assert dev == 0.0, dev
+    # Bit for bit wherever both kernels see the same live-prefix table.  The six-variant table is the maximum over the
+    # four classes, the one-variant table that of the base class: where a perturbed class's bound crosses a block
+    # boundary the base slice is summed in other chunks (or the set is routed to the other kernel) and the loss may
+    # differ by rounding -- measured on this population: nowhere.
+    rel = np.abs(a[ok] - b[ok]) / np.abs(b[ok])
+    assert (rel == 0.0).mean() >= 0.999 and rel.max() <= 1e-12, (float((rel == 0.0).mean()), float(rel.max()))
     # determinism and permutation equivariance of all 22 columns
     perm = torch.randperm(P, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(2))
     assert torch.equal(pr.normal_equations(X[perm]).view(torch.int64), neq[perm].view(torch.int64))  # NaN-safe

@@ -127,3 +127,65 @@ def test_maturity_entirely_off_the_grid(monkeypatch):
         ok = np.isfinite(ref)
         assert (np.abs(got - ref)[ok] <= 0.05 * (1e-10 * np.abs(ref[ok]) + 1e-12)).all()
     pr.close()
+
+
+@pytest.mark.parametrize("n_sets", [1, 2, 295, 296, 297, 591, 592, 593, 1183, 1185])
+def test_batch_sizes_around_the_launch_path_boundaries(monkeypatch, n_sets):
+    """Batch sizes on both sides of the split / persistent boundaries of the six-variant (2 x SMs x 2 CTAs = 592 on a
+    148-SM part) and one-variant (1184) direct-sum kernels and of the transform kernel (296): every row must equal the
+    row the same set gets in a large batch, bit for bit, and the two kernels must agree."""
+    import torch
+
+    from pde_b200 import BatchPricer
+
+    rng = np.random.default_rng(7)
+    K, T = np.tile(np.linspace(85, 115, 9), 5), np.repeat(np.array([0.1, 0.3, 0.6, 1.0, 1.7]), 9)
+    pr = BatchPricer("fft").set_surface(K, T, True, None, S0=S0, r=R, q=Q)
+    mk = pr.price(torch.tensor(np.array([[2.0, 0.04, 0.3, -0.7, 0.04]]), device="cuda:0")).cpu().numpy()[0]
+    pr.set_surface(K, T, True, np.maximum(mk * (1 + 0.01 * rng.normal(size=mk.size)), 0.01), S0=S0, r=R, q=Q)
+    big = _params(np.random.default_rng(11), 1400)
+    Xb = torch.tensor(big, device="cuda:0")
+    ref_loss, ref_neq = pr.objective(Xb).cpu().numpy(), pr.normal_equations(Xb).cpu().numpy()
+    X = Xb[:n_sets].contiguous()
+    loss, neq = pr.objective(X).cpu().numpy(), pr.normal_equations(X).cpu().numpy()
+    assert np.array_equal(loss, ref_loss[:n_sets], equal_nan=True)
+    assert np.array_equal(neq, ref_neq[:n_sets], equal_nan=True)
+    monkeypatch.setenv("HB_DIRECT", "0")
+    loss_t = pr.objective(X).cpu().numpy()
+    fin = np.isfinite(loss) & (loss != 1e10)
+    assert np.array_equal(loss == 1e10, loss_t == 1e10)
+    np.testing.assert_allclose(loss_t[fin], loss[fin], rtol=1e-10)
+    pr.close()
+
+
+def test_bound_limited_finite_difference_steps(monkeypatch):
+    """A degenerate box (a parameter on a bound of a narrow box) makes SciPy's step rule take steps as large as the box:
+    theta' / v0' then differ from the base by far more than 1e-8 and the class-0 expansion must fall back to the full
+    exponentials; both kernels against each other, and the Jacobian against a plain forward difference of prices."""
+    import torch
+
+    from pde_b200 import BatchPricer
+
+    K, T = np.tile(np.linspace(85, 115, 7), 3), np.repeat(np.array([0.25, 0.75, 1.5]), 7)
+    lb = np.array([1.0, 0.04, 0.3, -0.7, 0.04])
+    ub = np.array([3.0, 0.04 + 1e-9, 0.3 + 1e-3, -0.7 + 1e-12, 0.05])  # theta, rho: narrower than the default step
+    xs = np.array([[2.0, 0.04, 0.3, -0.7, 0.04], [3.0, 0.04 + 1e-9, 0.3 + 1e-3, -0.7 + 1e-12, 0.05],
+                   [1.0, 0.04 + 5e-10, 0.3005, -0.7, 0.045]])
+    X = torch.tensor(xs, device="cuda:0")
+    pr = BatchPricer("fft").set_surface(K, T, True, None, S0=S0, r=R, q=Q)
+    mk = pr.price(X[:1]).cpu().numpy()[0] * 1.01
+    pr.set_surface(K, T, True, mk, S0=S0, r=R, q=Q).set_bounds(lb, ub)
+    res, jac = (t.cpu().numpy() for t in pr.jacobian(X))
+    monkeypatch.setenv("HB_DIRECT", "0")
+    res_t, jac_t = (t.cpu().numpy() for t in pr.jacobian(X))
+    monkeypatch.delenv("HB_DIRECT")
+    p0 = pr.price(X).cpu().numpy()
+    tol_r = 0.05 * (1e-10 * np.abs(p0) + 1e-12) / mk[None, :]
+    assert (np.abs(res - res_t) <= tol_r).all()
+    assert np.isfinite(jac).all() and np.isfinite(jac_t).all()
+    scale = np.abs(jac_t).max(axis=1, keepdims=True) + 1e-300
+    # large steps: the finite difference is well conditioned, the kernels agree to rounding relative to the column scale;
+    # tiny steps (1e-12 on rho): bounded by the amplified price tolerance
+    bound = 2.0 * tol_r[:, :, None] / 1e-12 + 1e-9 * scale
+    assert (np.abs(jac - jac_t) <= bound).all()
+    pr.close()

@@ -412,6 +412,7 @@ fft_job_kernel(SurfaceDev S, GridConst gc, Bounds bd, const double* __restrict__
     // their number, both on the device; null = all P sets in order.  jtab[p][maturity]: live-prefix bound of that
     // launch (prefix_bound.cuh): grid points at or beyond it are exact zeros and are not evaluated.
     if (p_count) P = *p_count;
+    if (P <= 0) return;  // nothing was routed here: skip the table set-up
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* slices = reinterpret_cast<double2*>(smem_raw);
     double2* tw = slices + (size_t)gmax * N;

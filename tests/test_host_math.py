@@ -306,20 +306,22 @@ def test_live_prefix_bound_is_rigorous_and_tight(hm):
     ip = C.POINTER(C.c_int)
     # (the corners with sigma = 0.01 are the bound's weak spot: never asymptotic, |Im d| ~ Re d, prefix = whole grid --
     # such sets are routed to the transform kernel; tightness is asserted on the interior of the box)
-    for N, cut, X, tight in ((4096, -51.3, sob, 1.2), (4096, -51.3, np.array(corners), None), (4096, -36.0, sob[:32], 1.2),
-                             (4096, -120.0, sob[:32], 1.2), (16384, -52.0, sob[:24], 1.2)):
-        v = 0.25 * np.arange(float(N))
+    for N, cut, X, tight, eta, alpha in ((4096, -51.3, sob, 1.2, 0.25, 0.75), (4096, -51.3, np.array(corners), None, 0.25, 0.75),
+                                         (4096, -36.0, sob[:32], 1.2, 0.25, 0.75), (4096, -120.0, sob[:32], 1.2, 0.25, 0.75),
+                                         (16384, -52.0, sob[:24], 1.2, 0.25, 0.75), (4096, -45.0, sob[:32], 1.25, 0.125, 1.25),
+                                         (512, -48.0, sob[:32], None, 0.5, 1.0)):
+        v = eta * np.arange(float(N))
         tot_true = tot_bound = 0
         for x in X:
             for p in fd_variants(x[None, :])[[0, 1, 3, 4]]:  # base, kappa', sigma', rho'
                 p = np.ascontiguousarray(p, dtype=float)
                 J = np.zeros(Ts.size, dtype=np.int32)
-                nb = hm.hm_prefix_J(_p(p), C.c_int(Ts.size), _p(Ts), C.c_int(N), C.c_double(0.25), C.c_double(0.75),
+                nb = hm.hm_prefix_J(_p(p), C.c_int(Ts.size), _p(Ts), C.c_int(N), C.c_double(eta), C.c_double(alpha),
                                     C.c_double(S0), C.c_double(R), C.c_double(Q), C.c_double(cut), J.ctypes.data_as(ip))
                 assert 0 < nb <= 160
                 for t, T in enumerate(Ts):
                     er = np.empty(v.size)
-                    hm.hm_cf_exponent(_p(p), C.c_int(v.size), _p(v), C.c_double(-1.75), C.c_double(T), C.c_double(S0),
+                    hm.hm_cf_exponent(_p(p), C.c_int(v.size), _p(v), C.c_double(-(alpha + 1.0)), C.c_double(T), C.c_double(S0),
                                       C.c_double(R), C.c_double(Q), _p(er))
                     assert 1 <= J[t] <= N
                     tail = er[J[t]:]

@@ -242,25 +242,33 @@ __device__ __forceinline__ int direct_nsuper(int nblk) { return (nblk + kDSuper 
 __device__ __forceinline__ int direct_prefix(const PrefixBlock* fine, const PrefixBlock* super, const int* blk, int nblk,
                                              double T, double cst, const double* kts, const double* v0s, int nv,
                                              double cut) {
-    auto dead = [&](const PrefixBlock& b) -> bool {
-        const PrefixTerms t = prefix_terms(b, T);  // shared by the variants of the class
-        bool d = true;
-        for (int i = 0; i < nv; ++i) d = d && (prefix_ub_of(t, kts[i], v0s[i], cst) < cut - kPrefixMargin);
-        return d;
-    };
-    int k = nblk - 1;
-    for (int sb = direct_nsuper(nblk) - 1; sb >= 0; --sb) {
-        if (!dead(super[sb])) break;
-        k = kDSuper * sb - 1;
+    // ONE loop over super-blocks (from the end, while dead) and then fine blocks (downwards, while dead), with one call
+    // site of the bound: the bound's code is several hundred instructions, and a second inlined copy made the scan
+    // kernel miss its instruction cache 40 % of the time (profiles/r02_f_prefix_scan_kernel_bench_launch.txt)
+    int sb = direct_nsuper(nblk) - 1, k = nblk - 1;
+    bool in_super = true;
+    while (k >= 0) {
+        const PrefixTerms t = prefix_terms(in_super ? super[sb] : fine[k], T);  // shared by the variants of the class
+        bool dead = true;
+        for (int i = 0; i < nv; ++i) dead = dead && (prefix_ub_of(t, kts[i], v0s[i], cst) < cut - kPrefixMargin);
+        if (in_super) {
+            if (dead) {
+                k = kDSuper * sb - 1;  // every fine block of this super-block is dead
+                --sb;
+            } else {
+                in_super = false;  // its fine blocks, from the last one downwards
+            }
+        } else {
+            if (!dead) break;
+            --k;
+        }
     }
-    for (; k >= 0; --k)
-        if (!dead(fine[k])) break;
     return blk[k + 1];  // all blocks dead: blk[0] = 1 (point 0 is always evaluated)
 }
 // fine and super blocks of a class: entry i < nblk is fine block i, entry nblk + s super-block s
 __device__ __forceinline__ PrefixBlock direct_block_at(const PrefixClass& pc, const int* blk, int nblk, int i, double eta) {
-    if (i < nblk) return prefix_block(pc, eta * (double)blk[i], eta * (double)(blk[i + 1] - 1));
-    const int sb = i - nblk, k0 = kDSuper * sb, k1 = min(nblk, k0 + kDSuper);
+    const int k0 = (i < nblk) ? i : kDSuper * (i - nblk);
+    const int k1 = (i < nblk) ? i + 1 : min(nblk, k0 + kDSuper);
     return prefix_block(pc, eta * (double)blk[k0], eta * (double)(blk[k1] - 1));
 }
 

@@ -54,11 +54,19 @@ HB_HD PrefixClass prefix_class(const ClassConst& c, double alpha) {
 }
 
 // Re d(v), principal square root of P - i C v (cancellation-free on both signs of P)
+// square root by the branch-free routine of fp64_math.cuh (~1 ulp; the bound carries kPrefixMargin of slack)
+HB_HD double prefix_sqrt(double x) {
+    double s, r;
+    sqrt_rsqrt(x, &s, &r);
+    return s;
+}
 HB_HD double prefix_dr(const PrefixClass& p, double v) {
     const double zr = p.A0 + p.B * v * v, zi = p.C * v;
-    const double m = sqrt(zr * zr + zi * zi);
-    if (zr >= 0.0) return sqrt(0.5 * (m + zr));
-    return fabs(zi) / sqrt(2.0 * (m - zr));
+    const double m = prefix_sqrt(zr * zr + zi * zi);
+    // zr >= 0: sqrt((m + zr)/2);  zr < 0: |zi| / sqrt(2 (m - zr))  (the same number, without the cancellation)
+    double s, r;
+    sqrt_rsqrt((zr >= 0.0) ? 0.5 * (m + zr) : 2.0 * (m - zr), &s, &r);
+    return (zr >= 0.0) ? s : fabs(zi) * r;
 }
 
 // T-independent part of the bound on the block of grid points [va, vb]
@@ -88,26 +96,27 @@ HB_HD PrefixBlock prefix_block(const PrefixClass& p, double va, double vb) {
     const double sp = p.kp + b.dra;
     const bool ok = (sp > 0.0) && (b.dra > 0.0);
     const double wup = vb * vb + (2.0 * p.alpha + 1.0) * vb + p.alpha * (p.alpha + 1.0);
-    const double num_up = ok ? p.sigma2 * wup / sp : inf;
-    const double g_up = ok ? num_up / sp : inf;
-    b.q1_up = ok ? num_up / (2.0 * b.dra) : inf;
-    b.di_up = ok ? fabs(p.C) * vb / (2.0 * b.dra) : inf;
+    const double rsp = ok ? rcp_nr(sp) : 0.0, rdra = ok ? rcp_nr(2.0 * b.dra) : 0.0;
+    const double num_up = ok ? p.sigma2 * wup * rsp : inf;
+    const double g_up = ok ? num_up * rsp : inf;
+    b.q1_up = ok ? num_up * rdra : inf;
+    b.di_up = ok ? fabs(p.C) * vb * rdra : inf;
     const double D2a = fabs(p.A0) + p.B * va * va + fabs(p.C) * va;
     const double D2b = fabs(p.A0) + p.B * vb * vb + fabs(p.C) * vb;
     const double X2a = p.kp * p.kp + p.rs2 * va * va;
-    const double sd = sqrt(D2a), sx = sqrt(X2a);
-    const double s2v2 = p.sigma2 * va * va;
-    const double G2 = (sx + sd) * (sx + sd) / s2v2;
-    const double G1 = 2.0 * sd * (sx + sd) / s2v2;
+    const double sd = prefix_sqrt(D2a), sx = prefix_sqrt(X2a);
+    const double rs2v2 = rcp_nr(p.sigma2 * va * va);
+    const double G2 = (sx + sd) * (sx + sd) * rs2v2;
+    const double G1 = 2.0 * sd * (sx + sd) * rs2v2;
     b.gg = fmin(g_up, G2);
     const double one_g = fmin(1.0 + b.gg, G1);
-    b.l1g = 2.0 * log(one_g);
-    b.n1g = fmin(2.0 * sqrt(D2b) * b.gg, num_up * one_g);
+    b.l1g = 2.0 * log1p_nb(one_g - 1.0);
+    b.n1g = fmin(2.0 * prefix_sqrt(D2b) * b.gg, num_up * one_g);
     b.kp = p.kp;
     b.Pa = p.A0 + p.B * va * va;
     b.Pb = p.A0 + p.B * vb * vb;
     b.D2b = D2b;
-    b.bx = sqrt(p.rs2) * vb;
+    b.bx = fabs(p.rs) * vb;
     b.cv = fabs(p.C) * vb;
     b.swr = p.sigma2 * (va * va - p.alpha * (p.alpha + 1.0));
     b.swi = p.sigma2 * (2.0 * p.alpha + 1.0) * vb;
@@ -144,7 +153,7 @@ HB_HD PrefixTerms prefix_terms(const PrefixBlock& b, double T) {
     }
     PrefixTerms t;
     t.reB = b.nre * T + Lt;
-    t.reDq = gok ? b.nre + b.n1g * Ea / (1.0 - gE) : inf;
+    t.reDq = gok ? b.nre + b.n1g * Ea * rcp_nr(1.0 - gE) : inf;
     // (7) small |d T| (short maturities, small sigma: e is not small and the forms above lose the cancellation between
     // Re(num) and the rest).  With z = d T/2 (z^2 = d^2 T^2/4 is known without a square root):
     //   Re B = kp T - 2 log|sinh z / z| - 2 log|xi T/2 + z coth z|,      Dq = -sigma^2 w (T/2)/(xi T/2 + z coth z),
@@ -152,25 +161,28 @@ HB_HD PrefixTerms prefix_terms(const PrefixBlock& b, double T) {
     // with Re z^2 = P T^2/4 non-decreasing in v and |1 + x|^2 >= (1 + Re x)^2 + (|Im x| - |r|)^2.
     const double z2 = 0.25 * b.D2b * T * T;  // >= |z|^2 on the block
     if (z2 <= 2.0) {
-        const double r1 = z2 * z2 / (120.0 * (1.0 - z2 / 42.0));
-        const double r2 = z2 * z2 / (45.0 * (1.0 - z2 * 0.10132118364233778));
-        const double s1 = 1.0 + b.Pa * T * T / 24.0 - r1;
-        const double s2 = 1.0 + 0.5 * b.kp * T + b.Pa * T * T / 12.0 - r2;
+        const double T2 = T * T, c12 = 1.0 / 12.0, c24 = 1.0 / 24.0;
+        double q1r, q2r;  // 1 / (120 (1 - z2/42)),  1 / (45 (1 - z2/pi^2))
+        rcp2_nr(120.0 * (1.0 - z2 * (1.0 / 42.0)), 45.0 * (1.0 - z2 * 0.10132118364233778), &q1r, &q2r);
+        const double r1 = z2 * z2 * q1r;
+        const double r2 = z2 * z2 * q2r;
+        const double s1 = 1.0 + b.Pa * T2 * c24 - r1;
+        const double s2 = 1.0 + 0.5 * b.kp * T + b.Pa * T2 * c12 - r2;
         if (s1 > 0.0 && s2 > 0.0) {
             // imaginary parts: |Im(z^2/6)| >= |C| va T^2/24 - r1;  Im(xi T/2 + z^2/3) = -cim v, cim = rho sigma T/2 + C T^2/12
-            const double i1 = fmax(0.0, fabs(b.ca) * T * T / 24.0 - r1);
-            const double cima = 0.5 * b.rsa * T + b.ca * T * T / 12.0;  // cim va (signed)
+            const double i1 = fmax(0.0, fabs(b.ca) * T2 * c24 - r1);
+            const double cima = 0.5 * b.rsa * T + b.ca * T2 * c12;  // cim va (signed)
             const double i2 = fmax(0.0, fabs(cima) - r2);
             // log(m1) + log(m2) = log1p(m1 m2 - 1): the moduli are O(1) here (z2 <= 2)
             const double m1 = s1 * s1 + i1 * i1, m2 = s2 * s2 + i2 * i2;
             t.reB = fmin(t.reB, b.kp * T - log1p_nb(m1 * m2 - 1.0));
-            const double s2hi = 1.0 + 0.5 * b.kp * T + b.Pb * T * T / 12.0 + r2;
-            const double bup = 0.5 * b.bx * T + b.cv * T * T / 12.0 + r2;
+            const double s2hi = 1.0 + 0.5 * b.kp * T + b.Pb * T2 * c12 + r2;
+            const double bup = 0.5 * b.bx * T + b.cv * T2 * c12 + r2;
             // Re(w conj(den)) = Re w Re den + Im w Im den, Im w = -(2 alpha + 1) v, Im den = -cim v + Im r2:
             // the second product is >= swia (cim va - r2) when cim > 0, >= -swi bup always
             const double cross = (cima > r2) ? b.swia * (cima - r2) : -b.swi * bup;
             const double numer = b.swr * s2 + cross;
-            if (b.swr > 0.0 && numer > 0.0) t.reDq = fmin(t.reDq, -0.5 * T * numer / (s2hi * s2hi + bup * bup));
+            if (b.swr > 0.0 && numer > 0.0) t.reDq = fmin(t.reDq, -0.5 * T * numer * rcp_nr(s2hi * s2hi + bup * bup));
         }
     }
     return t;

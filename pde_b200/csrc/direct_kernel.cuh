@@ -52,13 +52,13 @@ namespace hb {
 #define HB_DNT1 256
 #endif
 #ifndef HB_DCAP1
-#define HB_DCAP1 256
+#define HB_DCAP1 192
 #endif
 #ifndef HB_DITEMS1
-#define HB_DITEMS1 192
+#define HB_DITEMS1 128
 #endif
 #ifndef HB_DCTAS1
-#define HB_DCTAS1 4
+#define HB_DCTAS1 5
 #endif
 #ifndef HB_DPULL
 #define HB_DPULL 64  // K1 tasks per trip to the queue (32 or 64)
@@ -102,9 +102,10 @@ template <bool ONEVAR>
 struct DirectCfg {
     static constexpr int V = ONEVAR ? 1 : 6;
     static constexpr int NCLS = ONEVAR ? 1 : 4;
-    // the one-variant kernel (prices, objective) holds 1/6 of the shared memory per point: four CTAs of 256 threads per SM
-    // measured +24 % over the six-variant kernel's shape (objective 49.5 -> 61.3 M slices/s; 128 x 6 gives 62.4 M but its
-    // finalize would sum over 128 threads: the loss column of the normal equations must equal the objective's bit for bit)
+    // the one-variant kernel (prices, objective) holds 1/6 of the shared memory per point: five CTAs of 256 threads per SM
+    // with waves of 768 points measured +30 % over the six-variant kernel's shape (objective 49.5 -> 64.5 M slices/s; 128
+    // threads x 6 CTAs is as fast but its finalize would sum over 128 threads: the loss column of the normal equations
+    // must equal the objective's bit for bit)
     static constexpr int NT = ONEVAR ? HB_DNT1 : HB_DNT;       // threads per CTA
     static constexpr int CTAS = ONEVAR ? HB_DCTAS1 : HB_DCTAS;  // CTAs per SM
     static constexpr int MAXP = ONEVAR ? kDMaxPairs1 : kDMaxPairs;      // conjugate pairs per maturity
